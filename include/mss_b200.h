@@ -1,0 +1,206 @@
+/* mss_b200 -- C ABI of the B200-native dense anomaly-scoring + exact OOD-evaluation path.
+ *
+ * The reference (gaozhitong/MultiShiftSeg) has no plugin / FFI layer: its boundary for this
+ * path is a handful of Python functions.  Each entry point below replaces one of them (cited
+ * as file:line relative to the reference root) and is what a ctypes / cffi / pybind stub on
+ * the reference side would bind.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every tensor pointer is a DEVICE pointer on the current
+ *     CUDA device unless the parameter name ends in `_host`;
+ *   - the caller owns every buffer, including workspaces; the library keeps no global mutable
+ *     state besides a thread-local error string, and is re-entrant (nn.DataParallel calls the
+ *     scoring functions from one thread per GPU);
+ *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*);
+ *   - return value: 0 = MSS_OK, >0 = a non-error outcome the reference also has
+ *     (MSS_EMPTY_CLASS <-> `eval_ood_measure` returning None), <0 = error; never throws/aborts.
+ *     `mss_last_error()` returns a thread-local human-readable message for the last <0 code.
+ *   - layouts are the reference's: NCHW contiguous fp32 logits, [B,Q,C+1] class logits,
+ *     [B,Q,h,w] mask logits, row-major score / label maps.
+ */
+#ifndef MSS_B200_H
+#define MSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MSS_API __attribute__((visibility("default")))
+#else
+#define MSS_API
+#endif
+
+/* return codes */
+#define MSS_OK 0
+#define MSS_EMPTY_CLASS 1        /* no ID or no OOD pixel: reference returns None (metric.py:176-180) */
+#define MSS_ERR_INVALID_ARG (-1)
+#define MSS_ERR_CUDA (-2)
+#define MSS_ERR_NAN (-3)         /* sklearn: ValueError("Input contains NaN.") */
+#define MSS_ERR_INF (-4)         /* sklearn: ValueError("Input contains infinity ...") */
+#define MSS_ERR_WORKSPACE (-5)   /* workspace / capacity too small */
+#define MSS_ERR_UNSUPPORTED (-6)
+
+/* label element types accepted wherever a `labels` pointer appears */
+#define MSS_LABEL_U8 1
+#define MSS_LABEL_I32 4
+#define MSS_LABEL_I64 8          /* what the reference testers pass (target.long(), test_deeplab.py:90) */
+
+/* which score maps mss_deeplab_score computes (bit mask); higher = more anomalous for all four */
+#define MSS_SCORE_ENERGY 1u      /* -(logsumexp_c x)            deepv3.py:251-253 */
+#define MSS_SCORE_MAXLOGIT 2u    /* -max_c x                    north_star extra score */
+#define MSS_SCORE_MSP 4u         /* 1 - max_c softmax(x)        north_star extra score */
+#define MSS_SCORE_ENTROPY 8u     /* -sum_c p_c log p_c          north_star extra score */
+
+MSS_API int mss_abi_version(void);
+MSS_API const char *mss_last_error(void);
+/* number of kernels this library has launched in the calling process (all threads); bench.py's gpu_launches */
+MSS_API int64_t mss_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Streaming evaluator buffers (device side of the tester loop, test_deeplab.py:84-101 /
+ * test_m2f.py:125-144: replaces per-batch .cpu().numpy() + np.concatenate with an on-device
+ * append of order-preserving keys for the valid pixels only).
+ * ------------------------------------------------------------------------------------------- */
+#define MSS_EVAL_STATE_BYTES 64
+typedef struct mss_eval_buffers {
+    uint32_t *keys;     /* [capacity] ascending key order == descending float32 score; -0.0 == +0.0 */
+    uint8_t *labs;      /* [capacity] 0 = in-distribution, 1 = OOD */
+    void *state;        /* MSS_EVAL_STATE_BYTES device bytes: {u64 count, u64 n_pos, u32 nan, u32 inf, ...} */
+    int64_t capacity;   /* in elements */
+} mss_eval_buffers;
+
+/* zero the state (count = 0) */
+MSS_API int mss_eval_reset(const mss_eval_buffers *ev, void *stream);
+/* metric.py:171-172 selection (label == id_in / id_out, everything else ignored) + key build; appends
+ * the valid pixels of (scores, labels)[0..n) to ev (order inside the buffer is unspecified). */
+MSS_API int mss_eval_append(const float *scores, const void *labels, int label_dtype, int64_t n,
+                    int64_t id_in, int64_t id_out, const mss_eval_buffers *ev, void *stream);
+/* read back {count, n_pos, nan_flag, inf_flag} (synchronises the stream) */
+MSS_API int mss_eval_state_host(const mss_eval_buffers *ev, int64_t out_host[4], void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a1, a2) DeepLabv3+ fused per-pixel scoring over NCHW fp32 logits [B, C, HW].
+ * Replaces DeepWV3Plus.energy_func (lib/network/deepv3/deepv3.py:251-253) and adds the three
+ * north_star scores.  Output pointers may be NULL for maps not selected in `which`.
+ * If `ev` is non-NULL, `labels` ([B*HW], label_dtype) must be given: the score selected by
+ * `key_which` (exactly one bit) is also appended to the evaluator for pixels with label
+ * id_in / id_out -- the ignore-label masking of metric.py:171-172 fused into the scoring pass.
+ * ------------------------------------------------------------------------------------------- */
+MSS_API int mss_deeplab_score(const float *logits, int64_t B, int C, int64_t HW, unsigned which,
+                      float *energy, float *maxlogit, float *msp, float *entropy,
+                      const void *labels, int label_dtype, int64_t id_in, int64_t id_out,
+                      unsigned key_which, const mss_eval_buffers *ev, void *stream);
+
+/* (a3, a4) bilinear resize of [NC, h, w] -> [NC, H, W] fp32.  align_corners=1 replaces mynn.Upsample
+ * (lib/network/deepv3/mynn.py:28-33); align_corners=0 replaces the F.interpolate calls at
+ * lib/network/mask2former/maskformer_model.py:264-277. */
+MSS_API int mss_upsample_bilinear(const float *in, int64_t NC, int h, int w, float *out, int H, int W,
+                          int align_corners, void *stream);
+
+/* deepv3.py:282-283 in one call: energy at head resolution [B,C,h,w] -> upsample (align_corners=True)
+ * -> anomaly score [B,H,W].  `scratch` holds B*h*w floats. */
+MSS_API int mss_deeplab_anomaly_score(const float *ood_logits, int64_t B, int C, int h, int w,
+                              float *scratch, float *score, int H, int W, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a4-a7) Mask2Former fused post-head inference.
+ *   cls_logits  [B, Q, C+1]        pred_logits / pred_logits_ood
+ *   mask_logits [B, Q, h, w]       pred_masks / pred_masks_ood at decoder resolution
+ * computes, without ever materialising the [Q, Hp, Wp] tensor,
+ *   P = softmax(cls)[..., :C]; S = sigmoid(bilinear(mask_logits -> Hp x Wp, align_corners=False));
+ *   semseg[b, c, y, x] = sum_q P[b,q,c] S[b,q,y,x]                     (maskformer_model.py:343-345)
+ *   extra[b][k]        = score_k * S[b, q_k]   for the kept queries     (maskformer_model.py:346-352)
+ *   anomaly[b, y, x]   = 1 - max_c semseg[b, c, y, x]                   (train_m2f.py:402-407)
+ * cropped to y < Hc, x < Wc (sem_seg_postprocess crop, maskformer_model.py:299-300; train_m2f.py:406).
+ * Hp == h and Wp == w is the "already upsampled" case (drop-in semantic_inference / get_anomaly_score).
+ * Any of semseg / anomaly may be NULL (not both).  Extra channels: keep_idx [B, Q] int32 lists, per
+ * image, the kept query indices (first keep_count[b] entries valid; keep_count is a DEVICE int32 [B]) and
+ * keep_score [B, Q] holds softmax(cls).max(-1) per query; plane k of image b goes to
+ * extra + b*extra_batch_stride + k*Hc*Wc.  Pass NULL to skip.  semseg_batch_stride = elements between
+ * consecutive images' semseg blocks (>= C*Hc*Wc), so the caller can place the extra planes right behind
+ * the C planes of the same image (the torch.cat layout of maskformer_model.py:352).
+ * workspace: mss_m2f_workspace_bytes(B, Q, C) device bytes.  flags: MSS_M2F_FORCE_GENERIC skips the
+ * TMA-staged x4 kernel (testing).  Limits: Q <= 128, C <= 32; the fast path needs C == 19, Hp == 4h,
+ * Wp == 4w, w % 4 == 0 (always true for the model: stride 4, size divisibility 32).
+ * ------------------------------------------------------------------------------------------- */
+#define MSS_M2F_FORCE_GENERIC 1u
+MSS_API size_t mss_m2f_workspace_bytes(int64_t B, int Q, int C);
+MSS_API int mss_m2f_semantic_inference(const float *cls_logits, const float *mask_logits,
+                               int64_t B, int Q, int C, int h, int w, int Hp, int Wp, int Hc, int Wc,
+                               float *semseg, int64_t semseg_batch_stride, float *anomaly,
+                               const int32_t *keep_idx, const float *keep_score,
+                               const int32_t *keep_count, float *extra, int64_t extra_batch_stride,
+                               void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a9-a13) exact, tie-aware AUROC / AP / FPR@95TPR.
+ * Replaces eval_ood_measure (lib/utils/metric.py:170-180) and everything below it
+ * (get_measures :130-153, sklearn roc_auc_score / average_precision_score at :142/:146,
+ * fpr_and_fdr_at_recall :87-127).  Results are bit-identical to that computation.
+ * ------------------------------------------------------------------------------------------- */
+/* bytes of device workspace for n candidate pixels (one-shot) or n stored keys (from evaluator) */
+MSS_API size_t mss_ood_metrics_workspace_bytes(int64_t n);
+
+/* one-shot: scores [n] fp32 + labels [n]  ->  out_host = {AUROC, AP, FPR95}, counts_host = {P, N, T, T_roc}.
+ * Returns MSS_EMPTY_CLASS when there is no label==id_in or no label==id_out pixel, MSS_ERR_NAN /
+ * MSS_ERR_INF when a valid score is not finite.  Synchronises `stream`. */
+MSS_API int mss_ood_metrics(const float *scores, const void *labels, int label_dtype, int64_t n,
+                    int64_t id_in, int64_t id_out, void *workspace, size_t workspace_bytes,
+                    double out_host[3], int64_t counts_host[4], void *stream);
+
+/* same, from keys accumulated in an evaluator (keys/labs are sorted in place). */
+MSS_API int mss_ood_metrics_from_eval(const mss_eval_buffers *ev, void *workspace, size_t workspace_bytes,
+                              double out_host[3], int64_t counts_host[4], void *stream);
+
+/* ---- stage-level entry points (used by the multi-GPU evaluator, which interleaves them with
+ * NCCL collectives issued through torch.distributed) ---------------------------------------- */
+/* stable LSD radix sort of n (key, label) pairs, ascending key, in place (uses workspace as the
+ * second buffer). */
+MSS_API size_t mss_sort_pairs_workspace_bytes(int64_t n);
+MSS_API int mss_sort_pairs(uint32_t *keys, uint8_t *labs, int64_t n, void *workspace, size_t workspace_bytes,
+                   void *stream);
+/* histogram of the top `bits` (<= 16) key bits: hist[1 << bits] int64, overwritten (splitter selection) */
+MSS_API int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int64_t *hist, void *stream);
+/* stable partition of (key,label) pairs into `parts` (<= 256) destination ranges:
+ * dest(key) = #{ j : key >= splitters[j] }, splitters ascending device array [parts-1].
+ * out_counts_host[parts] receives the bucket sizes (synchronises the stream). */
+MSS_API size_t mss_partition_workspace_bytes(int64_t n);
+MSS_API int mss_partition_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n, const uint32_t *splitters,
+                        int parts, uint32_t *keys_out, uint8_t *labs_out, int64_t *out_counts_host,
+                        void *workspace, size_t workspace_bytes, void *stream);
+/* sorted pairs -> per distinct key cumulative counts: tps[k] = pos_before + #pos at positions <= end_k,
+ * fps[k] = idx_before + end_k + 1 - tps[k] (int64).  tps/fps need room for n entries.  *T_host = number
+ * of distinct keys, pn_host = {#pos, #neg} of this slice (synchronises the stream). */
+MSS_API size_t mss_counts_workspace_bytes(int64_t n);
+MSS_API int mss_counts_from_sorted(const uint32_t *keys, const uint8_t *labs, int64_t n, int64_t pos_before,
+                           int64_t idx_before, int64_t *tps, int64_t *fps, int64_t *T_host,
+                           int64_t pn_host[2], void *workspace, size_t workspace_bytes, void *stream);
+/* float64 tail over device int64 (tps, fps)[T]: out_host = {AUROC, AP, FPR95}; *T_roc_host = points kept
+ * by roc_curve(drop_intermediate=True).  recall_level is 0.95 everywhere in the reference
+ * (metric.py:130).  Replays numpy's pairwise summation tree exactly. */
+MSS_API size_t mss_tail_workspace_bytes(int64_t T);
+MSS_API int mss_metrics_tail(const int64_t *tps, const int64_t *fps, int64_t T, double recall_level,
+                     void *workspace, size_t workspace_bytes, double out_host[3], int64_t *T_roc_host,
+                     void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer entry points: what a reference-side caller holding numpy / CPU tensors would call.
+ * Inputs and outputs are HOST pointers (pinned memory recommended); the library stages them
+ * through caller-provided device scratch in chunks, overlapping H2D, kernel and D2H on internal
+ * streams forked from `stream`.  These are the `e2e` legs of bench.py.
+ * ------------------------------------------------------------------------------------------- */
+MSS_API size_t mss_deeplab_score_host_scratch_bytes(int64_t B, int C, int64_t HW, unsigned which);
+MSS_API int mss_deeplab_score_host(const float *logits_host, int64_t B, int C, int64_t HW, unsigned which,
+                           float *energy_host, float *maxlogit_host, float *msp_host, float *entropy_host,
+                           void *device_scratch, size_t scratch_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSS_B200_H */

@@ -1,0 +1,124 @@
+// Shared device / host helpers for libmss_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/mss_b200.h"
+
+namespace mss {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define MSS_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            mss::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                           __LINE__);                                                          \
+            return MSS_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define MSS_CHECK_LAUNCH()                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            mss::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),         \
+                           __FILE__, __LINE__);                                                \
+            return MSS_ERR_CUDA;                                                               \
+        }                                                                                      \
+        mss::count_launch();                                                                   \
+    } while (0)
+
+#define MSS_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            mss::set_error(__VA_ARGS__);                                                       \
+            return MSS_ERR_INVALID_ARG;                                                        \
+        }                                                                                      \
+    } while (0)
+
+int sm_count();  // SMs of the current device (148 on B200), cached per device
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over a caller-provided workspace
+struct Carver {
+    char *base;
+    size_t off = 0, cap;
+    Carver(void *p, size_t bytes) : base((char *)p), cap(bytes) {}
+    template <typename T>
+    T *take(size_t n) {
+        off = align_up(off, 256);
+        T *r = (T *)(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+// ---- evaluator state (device) -----------------------------------------------------------------
+struct EvalState {
+    unsigned long long count;  // valid pixels appended so far
+    unsigned long long n_pos;  // of which OOD
+    unsigned int nan_flag;
+    unsigned int inf_flag;
+    unsigned long long overflow;  // appends dropped because capacity was exceeded
+    unsigned long long pad[4];
+};
+static_assert(sizeof(EvalState) == MSS_EVAL_STATE_BYTES, "EvalState size is ABI");
+
+#ifdef __CUDACC__
+// ---- device helpers ---------------------------------------------------------------------------
+// streaming 128-bit global load: read-only path, do not allocate in L1 (data is touched once)
+__device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream_f4(float *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream_f1(float *p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// float32 score -> uint32 key whose ascending order is the descending score order;
+// -0.0 and +0.0 collapse to one key (np.diff(y_score) == 0 between them: one threshold).
+__device__ __forceinline__ uint32_t score_key_desc(float f) {
+    uint32_t u = __float_as_uint(f);
+    if (u == 0x80000000u) u = 0u;
+    uint32_t asc = (u >> 31) ? ~u : (u | 0x80000000u);
+    return ~asc;
+}
+
+__device__ __forceinline__ long long load_label(const void *labels, int dtype, long long i) {
+    if (dtype == MSS_LABEL_U8) return ((const uint8_t *)labels)[i];
+    if (dtype == MSS_LABEL_I32) return ((const int32_t *)labels)[i];
+    return ((const long long *)labels)[i];
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+#endif  // __CUDACC__
+
+}  // namespace mss

@@ -1,0 +1,410 @@
+// Stable LSD radix sort of (uint32 key, uint8 label) pairs -- the GPU replacement for the three
+// full argsorts the reference performs per evaluation (sklearn _ranking.py:909 inside roc_auc_score and
+// again inside average_precision_score, plus np.argsort(kind="mergesort") at lib/utils/metric.py:103).
+//
+// "Onesweep": one upfront histogram of all four 8-bit digits, then four scatter passes, each reading
+// and writing every pair exactly once; the cross-tile digit offsets come from a decoupled look-back
+// over per-tile status words instead of a separate scan pass.
+//   HBM traffic per pair: 4 (histogram read) + 4 x (4+1 read + 4+1 write) = 44 B.
+// Tile = 256 threads x 16 keys.  Ranking inside a tile is stable and atomics-free: keys are
+// warp-striped, each warp ranks its 512 keys item by item with match.any, warps are combined by a
+// per-digit prefix over the 8 warps.
+//
+// The same scatter kernel, with the digit replaced by "which key range does this key fall in"
+// (SplitterDigit), is the local half of the multi-GPU key-range exchange (mss_partition_pairs).
+#include "common.cuh"
+
+namespace mss {
+
+constexpr int RADIX = 256;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_IPT = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+
+struct ShiftDigit {
+    int shift;
+    __device__ __forceinline__ unsigned operator()(uint32_t k) const { return (k >> shift) & 255u; }
+};
+
+// dest(key) = #{ j : key >= splitter[j] }  (splitters ascending, parts-1 of them, parts <= 256)
+struct SplitterDigit {
+    const uint32_t *spl;
+    int nspl;
+    __device__ __forceinline__ unsigned operator()(uint32_t k) const {
+        int lo = 0, hi = nspl;  // first j with spl[j] > k
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (__ldg(spl + mid) <= k) lo = mid + 1; else hi = mid;
+        }
+        return (unsigned)lo;
+    }
+};
+
+// ---- upfront histogram of the four digits ------------------------------------------------------------
+// Upper digits of real score distributions are extremely skewed (sign + exponent bits), so shared
+// atomics would serialise 32-way; match.any aggregates equal digits inside the warp first.
+__global__ void __launch_bounds__(512)
+radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned long long *__restrict__ hist) {
+    __shared__ unsigned s_hist[4][RADIX];
+    for (int i = threadIdx.x; i < 4 * RADIX; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long iters = (n + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lt = lanemask_lt();
+    for (long long it = 0; it < iters; it++, i += stride) {
+        const bool valid = i < n;
+        const uint32_t k = valid ? __ldg(keys + i) : 0u;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const unsigned d = (k >> (8 * p)) & 255u;
+                const unsigned peers = __match_any_sync(act, d);
+                if ((peers & lt) == 0) atomicAdd(&s_hist[p][d], __popc(peers));
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 4 * RADIX; j += blockDim.x) {
+        unsigned c = (&s_hist[0][0])[j];
+        if (c) atomicAdd(hist + j, (unsigned long long)c);
+    }
+}
+
+// hist[4][256] -> exclusive prefix per pass (in place), one warp-scan per pass
+__global__ void __launch_bounds__(RADIX)
+radix_scan_bins_kernel(unsigned long long *__restrict__ hist, int passes) {
+    __shared__ unsigned long long s_warp[RADIX / 32];
+    for (int p = 0; p < passes; p++) {
+        unsigned long long v = hist[p * RADIX + threadIdx.x], inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((threadIdx.x & 31) >= d) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        unsigned long long base = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += s_warp[w];
+        hist[p * RADIX + threadIdx.x] = base + inc - v;
+        __syncthreads();
+    }
+}
+
+// ---- one scatter pass -----------------------------------------------------------------------------
+// tile_status[tile][digit]: bits 63..62 = 0 empty / 1 tile count / 2 inclusive prefix, low 62 bits = value.
+constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <typename DigitFn>
+__global__ void __launch_bounds__(SORT_THREADS, 3)
+onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out,
+                     const uint8_t *__restrict__ vals_in, uint8_t *__restrict__ vals_out, long long n,
+                     const unsigned long long *__restrict__ bin_base, unsigned long long *tile_status,
+                     unsigned *tile_counter, DigitFn digit_of) {
+    __shared__ __align__(16) uint32_t s_keys[SORT_TILE];
+    __shared__ __align__(16) uint8_t s_vals[SORT_TILE];
+    __shared__ unsigned s_warp_hist[SORT_WARPS][RADIX];
+    __shared__ unsigned s_tile_start[RADIX];
+    __shared__ unsigned long long s_global[RADIX];
+    __shared__ unsigned s_scan[SORT_WARPS];
+    __shared__ unsigned s_tile;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) s_warp_hist[w][tid] = 0;
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const long long tile_base = (long long)tile * SORT_TILE;
+    const int tile_n = (int)min((long long)SORT_TILE, n - tile_base);
+
+    // labels of the tile: one coalesced 16-byte load per thread, staged in smem
+    {
+        const long long b = tile_base + (long long)tid * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (b + 16 <= n && ((((uintptr_t)vals_in) & 15) == 0)) {
+            v = *reinterpret_cast<const uint4 *>(vals_in + b);
+        } else {
+            uint8_t *pv = reinterpret_cast<uint8_t *>(&v);
+            for (int j = 0; j < 16; j++) pv[j] = (b + j < n) ? vals_in[b + j] : 0;
+        }
+        *reinterpret_cast<uint4 *>(s_vals + tid * 16) = v;
+    }
+
+    // keys, warp-striped: item i of lane l in warp w sits at w*512 + i*32 + l
+    uint32_t key[SORT_IPT];
+    const int wbase = warp * (32 * SORT_IPT) + lane;
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        const int idx = wbase + i * 32;
+        key[i] = (idx < tile_n) ? __ldg(keys_in + tile_base + idx) : 0u;
+    }
+    __syncthreads();   // s_vals staged, s_warp_hist zeroed
+
+    uint8_t val[SORT_IPT];
+    unsigned short rank[SORT_IPT];
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        const int idx = wbase + i * 32;
+        const bool valid = idx < tile_n;
+        val[i] = s_vals[idx];
+        const unsigned d = valid ? digit_of(key[i]) : RADIX;   // invalid lanes form their own group
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned below = __popc(peers & lt);
+        unsigned old = 0;
+        if (below == 0 && valid) {
+            old = s_warp_hist[warp][d];
+            s_warp_hist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+        rank[i] = (unsigned short)(old + below);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d: prefix over the 8 warps for digit d, tile count, publish, look back
+    {
+        const unsigned d = tid;
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            unsigned c = s_warp_hist[w][d];
+            s_warp_hist[w][d] = tot;
+            tot += c;
+        }
+        unsigned long long *my = tile_status + (size_t)tile * RADIX + d;
+        if (tile == 0) st_status(my, FLAG_INC | tot);
+        else st_status(my, FLAG_AGG | tot);
+
+        // exclusive scan of tot over the 256 digits
+        unsigned inc = tot;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, inc, s);
+            if (lane >= s) inc += t;
+        }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        unsigned wsum = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) wsum += (w < (int)warp) ? s_scan[w] : 0u;
+        const unsigned start = wsum + inc - tot;
+        s_tile_start[d] = start;
+
+        unsigned long long prefix = 0;
+        if (tile > 0) {
+            long long t = (long long)tile - 1;
+            while (true) {
+                unsigned long long st = ld_status(tile_status + (size_t)t * RADIX + d);
+                if ((st >> 62) == 0) continue;           // predecessor not published yet
+                prefix += st & VAL_MASK;
+                if ((st >> 62) == 2) break;
+                t--;
+            }
+            st_status(my, FLAG_INC | (prefix + tot));
+        }
+        s_global[d] = bin_base[d] + prefix - start;
+    }
+    __syncthreads();
+
+    // scatter into tile-sorted order in smem
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        const int idx = wbase + i * 32;
+        if (idx < tile_n) {
+            const unsigned d = digit_of(key[i]);
+            const unsigned pos = s_tile_start[d] + s_warp_hist[warp][d] + rank[i];
+            s_keys[pos] = key[i];
+            s_vals[pos] = val[i];   // safe: every s_vals read happened before the last __syncthreads
+        }
+    }
+    __syncthreads();
+
+    // coalesced write-out: equal digits are contiguous in smem and in the output
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        const int p = i * SORT_THREADS + tid;
+        if (p < tile_n) {
+            const uint32_t k = s_keys[p];
+            const unsigned long long o = s_global[digit_of(k)] + p;
+            keys_out[o] = k;
+            vals_out[o] = s_vals[p];
+        }
+    }
+}
+
+// top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536, global atomics after
+// per-warp aggregation; adjacent pixels of a score map tend to share high key bits)
+__global__ void __launch_bounds__(256)
+keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift, unsigned long long *hist) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long iters = (n + stride - 1) / stride;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lt = lanemask_lt();
+    for (long long it = 0; it < iters; it++, i += stride) {
+        const bool valid = i < n;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned b = __ldg(keys + i) >> shift;
+            const unsigned peers = __match_any_sync(act, b);
+            if ((peers & lt) == 0) atomicAdd(hist + b, (unsigned long long)__popc(peers));
+        }
+    }
+}
+
+static size_t sort_tiles(int64_t n) { return (size_t)((n + SORT_TILE - 1) / SORT_TILE); }
+
+struct SortWs {
+    uint32_t *keys_alt;
+    uint8_t *vals_alt;
+    unsigned long long *hist;      // [4][256]
+    unsigned *counters;            // [4] (+pad)
+    unsigned long long *status;    // [4][tiles][256]
+    size_t zero_bytes;             // hist..status are contiguous: one memset
+    char *zero_base;
+};
+
+static bool carve_sort(void *ws, size_t bytes, int64_t n, int passes, SortWs &o) {
+    Carver c(ws, bytes);
+    o.keys_alt = c.take<uint32_t>((size_t)n);
+    o.vals_alt = c.take<uint8_t>((size_t)n);
+    o.hist = c.take<unsigned long long>(4 * RADIX);
+    o.zero_base = (char *)o.hist;
+    o.counters = c.take<unsigned>(64);
+    o.status = c.take<unsigned long long>((size_t)passes * sort_tiles(n) * RADIX);
+    o.zero_bytes = (size_t)((char *)(o.status + (size_t)passes * sort_tiles(n) * RADIX) - o.zero_base);
+    return c.ok();
+}
+
+}  // namespace mss
+
+using namespace mss;
+
+extern "C" size_t mss_sort_pairs_workspace_bytes(int64_t n) {
+    if (n < 0) n = 0;
+    return align_up((size_t)n * 4, 256) + align_up((size_t)n, 256) + 4 * RADIX * 8 + 256 + 256 +
+           4 * sort_tiles(n) * RADIX * 8 + 2048;
+}
+
+extern "C" int mss_sort_pairs(uint32_t *keys, uint8_t *labs, int64_t n, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+    MSS_REQUIRE(n >= 0, "mss_sort_pairs: n < 0");
+    if (n <= 1) return MSS_OK;
+    MSS_REQUIRE(keys && labs && workspace, "mss_sort_pairs: null pointer");
+    SortWs w;
+    if (!carve_sort(workspace, workspace_bytes, n, 4, w)) {
+        set_error("mss_sort_pairs: workspace too small (%zu < %zu)", workspace_bytes, mss_sort_pairs_workspace_bytes(n));
+        return MSS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    MSS_CHECK_CUDA(cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, st));
+    const size_t tiles = sort_tiles(n);
+    MSS_REQUIRE(tiles < (1ull << 31), "mss_sort_pairs: n too large");
+    int hgrid = (int)std::min<long long>((n + 511) / 512, (long long)sm_count() * 4);
+    radix_histogram_kernel<<<hgrid, 512, 0, st>>>(keys, n, w.hist);
+    MSS_CHECK_LAUNCH();
+    radix_scan_bins_kernel<<<1, RADIX, 0, st>>>(w.hist, 4);
+    MSS_CHECK_LAUNCH();
+    uint32_t *kin = keys, *kout = w.keys_alt;
+    uint8_t *vin = labs, *vout = w.vals_alt;
+    for (int p = 0; p < 4; p++) {
+        onesweep_pass_kernel<ShiftDigit><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
+            kin, kout, vin, vout, n, w.hist + p * RADIX, w.status + (size_t)p * tiles * RADIX, w.counters + p,
+            ShiftDigit{8 * p});
+        MSS_CHECK_LAUNCH();
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    return MSS_OK;   // 4 passes: the result is back in (keys, labs)
+}
+
+extern "C" int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int64_t *hist, void *stream) {
+    MSS_REQUIRE(bits >= 1 && bits <= 16 && hist, "mss_keys_histogram: bits must be 1..16");
+    MSS_REQUIRE(n >= 0, "mss_keys_histogram: n < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    MSS_CHECK_CUDA(cudaMemsetAsync(hist, 0, sizeof(int64_t) << bits, st));
+    if (n == 0) return MSS_OK;
+    MSS_REQUIRE(keys, "mss_keys_histogram: null keys");
+    int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+    keys_histogram_kernel<<<grid, 256, 0, st>>>(keys, n, 32 - bits, (unsigned long long *)hist);
+    MSS_CHECK_LAUNCH();
+    return MSS_OK;
+}
+
+extern "C" size_t mss_partition_workspace_bytes(int64_t n) {
+    if (n < 0) n = 0;
+    return RADIX * 8 + 256 + 256 + 2 * sort_tiles(n) * RADIX * 8 + 4096;
+}
+
+// exclusive prefix of the bucket sizes
+__global__ void __launch_bounds__(RADIX)
+partition_bases_kernel(const unsigned long long *counts, unsigned long long *base) {
+    __shared__ unsigned long long sh[RADIX];
+    sh[threadIdx.x] = counts[threadIdx.x];
+    __syncthreads();
+    unsigned long long b = 0;
+    for (int j = 0; j < (int)threadIdx.x; j++) b += sh[j];
+    base[threadIdx.x] = b;
+}
+
+__global__ void __launch_bounds__(256)
+partition_count_tiles_kernel(const uint32_t *__restrict__ keys, long long n, SplitterDigit dg,
+                             unsigned long long *__restrict__ counts) {
+    __shared__ unsigned s_c[RADIX];
+    s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&s_c[dg(__ldg(keys + i))], 1u);
+    __syncthreads();
+    if (s_c[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_c[threadIdx.x]);
+}
+
+extern "C" int mss_partition_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n, const uint32_t *splitters,
+                                   int parts, uint32_t *keys_out, uint8_t *labs_out, int64_t *out_counts_host,
+                                   void *workspace, size_t workspace_bytes, void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= RADIX, "mss_partition_pairs: parts must be 1..256");
+    MSS_REQUIRE(n >= 0 && out_counts_host, "mss_partition_pairs: bad arguments");
+    for (int j = 0; j < parts; j++) out_counts_host[j] = 0;
+    if (n == 0) return MSS_OK;
+    MSS_REQUIRE(keys && labs && keys_out && labs_out && workspace && (parts == 1 || splitters),
+                "mss_partition_pairs: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tiles = sort_tiles(n);
+    Carver c(workspace, workspace_bytes);
+    unsigned long long *base = c.take<unsigned long long>(RADIX);
+    unsigned long long *counts = c.take<unsigned long long>(RADIX);
+    unsigned *counter = c.take<unsigned>(64);
+    unsigned long long *status = c.take<unsigned long long>(tiles * RADIX);
+    if (!c.ok()) {
+        set_error("mss_partition_pairs: workspace too small (%zu < %zu)", workspace_bytes, mss_partition_workspace_bytes(n));
+        return MSS_ERR_WORKSPACE;
+    }
+    MSS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)((char *)(status + tiles * RADIX) - (char *)workspace), st));
+    SplitterDigit dg{splitters, parts - 1};
+    int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+    partition_count_tiles_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
+    MSS_CHECK_LAUNCH();
+    partition_bases_kernel<<<1, RADIX, 0, st>>>(counts, base);
+    MSS_CHECK_LAUNCH();
+    onesweep_pass_kernel<SplitterDigit><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
+        keys, keys_out, labs, labs_out, n, base, status, counter, dg);
+    MSS_CHECK_LAUNCH();
+    unsigned long long h[RADIX];
+    MSS_CHECK_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, st));
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < parts; j++) out_counts_host[j] = (int64_t)h[j];
+    return MSS_OK;
+}

@@ -1,0 +1,140 @@
+"""DeepLabv3+ scoring: drop-ins for ``DeepWV3Plus.energy_func`` (lib/network/deepv3/deepv3.py:251-253),
+``mynn.Upsample`` (lib/network/deepv3/mynn.py:28-33) and the OOD-head tail of the forward
+(deepv3.py:282-283), plus the fused multi-score entry point named by the north star
+(energy / max-logit / max-softmax / entropy in one pass over the logits).
+
+All functions take and return CUDA tensors; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+__all__ = ["energy_func", "Upsample", "anomaly_score", "score_maps", "SCORES"]
+
+SCORES = ("energy", "maxlogit", "msp", "entropy")
+
+
+def _prep_logits(logit: torch.Tensor) -> torch.Tensor:
+    L.require_cuda(logit, "logit")
+    if logit.dim() < 2:
+        raise ValueError("logit must be [B, C, ...]")
+    if logit.dtype != torch.float32:
+        logit = logit.float()
+    return logit.contiguous()
+
+
+def score_maps(logit: torch.Tensor, which: Iterable[str] = ("energy",), *, labels: Optional[torch.Tensor] = None,
+               evaluator=None, key: Optional[str] = None, id_in: int = 0, id_out: int = 1) -> Dict[str, torch.Tensor]:
+    """One pass over NCHW logits -> the requested score maps ``{name: [B, *spatial]}``.
+
+    With ``evaluator`` (a ``metric.PairBuffer``) and ``labels`` ([B, *spatial], uint8/int32/int64) the map
+    named ``key`` is also appended -- for pixels labelled ``id_in`` / ``id_out`` only -- to the on-device
+    evaluator inside the same kernel (ignore-label masking fused into scoring).
+    """
+    logit = _prep_logits(logit)
+    which = tuple(which)
+    mask = 0
+    for w in which:
+        if w not in L.SCORE_BITS:
+            raise ValueError(f"unknown score {w!r}; choose from {SCORES}")
+        mask |= L.SCORE_BITS[w]
+    if mask == 0:
+        raise ValueError("no score selected")
+    B, Cn = logit.shape[0], logit.shape[1]
+    spatial = tuple(logit.shape[2:])
+    HW = 1
+    for s in spatial:
+        HW *= s
+    out = {w: torch.empty((B,) + spatial, dtype=torch.float32, device=logit.device) for w in which}
+    ev_ref, lab_ptr, lab_code, key_bit = None, 0, 0, 0
+    if evaluator is not None:
+        if labels is None or key is None:
+            raise ValueError("evaluator needs labels and key")
+        L.require_cuda(labels, "labels")
+        labels = labels.contiguous()
+        if labels.numel() != B * HW:
+            raise ValueError("labels must have one entry per pixel")
+        if key not in which:
+            raise ValueError("key must be one of the computed scores")
+        ev_ref, lab_ptr, lab_code, key_bit = C.byref(evaluator.c), labels.data_ptr(), L.label_code(labels), L.SCORE_BITS[key]
+    with torch.cuda.device(logit.device):
+        rc = L.load().mss_deeplab_score(
+            logit.data_ptr(), B, Cn, HW, mask, L.ptr(out.get("energy")), L.ptr(out.get("maxlogit")),
+            L.ptr(out.get("msp")), L.ptr(out.get("entropy")), lab_ptr, lab_code, id_in, id_out, key_bit, ev_ref,
+            L.stream_ptr(logit.device))
+    L.check(rc, "mss_deeplab_score")
+    return out
+
+
+def energy_func(logit: torch.Tensor) -> torch.Tensor:
+    """``-(1. * torch.logsumexp(logit, dim=1))`` -- deepv3.py:251-253 (call as a function, or bind it
+    as the model's method: ``DeepWV3Plus.energy_func = lambda self, x: energy_func(x)``)."""
+    return score_maps(logit, ("energy",))["energy"]
+
+
+def Upsample(x: torch.Tensor, size: Sequence[int], align_corners: bool = True) -> torch.Tensor:
+    """mynn.py:28-33: ``F.interpolate(x, size=size, mode='bilinear', align_corners=True)`` for [N,C,h,w]."""
+    L.require_cuda(x, "x")
+    if x.dim() != 4:
+        raise ValueError("Upsample expects [N, C, h, w]")
+    x = x.float().contiguous() if x.dtype != torch.float32 else x.contiguous()
+    N, Cn, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((N, Cn, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.load().mss_upsample_bilinear(x.data_ptr(), N * Cn, h, w, out.data_ptr(), H, W,
+                                            1 if align_corners else 0, L.stream_ptr(x.device))
+    L.check(rc, "mss_upsample_bilinear")
+    return out
+
+
+def anomaly_score(ood_logit: torch.Tensor, size: Sequence[int]) -> torch.Tensor:
+    """deepv3.py:283: ``Upsample(self.energy_func(dec2).unsqueeze(1), x_size[2:]).squeeze(1)``."""
+    ood_logit = _prep_logits(ood_logit)
+    if ood_logit.dim() != 4:
+        raise ValueError("ood_logit must be [B, C, h, w]")
+    B, Cn, h, w = ood_logit.shape
+    H, W = int(size[0]), int(size[1])
+    scratch = torch.empty((B, h, w), dtype=torch.float32, device=ood_logit.device)
+    out = torch.empty((B, H, W), dtype=torch.float32, device=ood_logit.device)
+    with torch.cuda.device(ood_logit.device):
+        rc = L.load().mss_deeplab_anomaly_score(ood_logit.data_ptr(), B, Cn, h, w, scratch.data_ptr(), out.data_ptr(),
+                                                H, W, L.stream_ptr(ood_logit.device))
+    L.check(rc, "mss_deeplab_anomaly_score")
+    return out
+
+
+def score_maps_host(logits_host: torch.Tensor, which: Iterable[str] = ("energy",), scratch: Optional[torch.Tensor] = None,
+                    out: Optional[Dict[str, torch.Tensor]] = None, device=None) -> Dict[str, torch.Tensor]:
+    """Host-buffer variant (what a caller holding CPU tensors uses; bench.py's e2e leg): logits and the
+    returned maps live in (preferably pinned) host memory, the library pipelines H2D / kernel / D2H."""
+    if logits_host.is_cuda:
+        raise ValueError("score_maps_host takes a CPU tensor; use score_maps for CUDA tensors")
+    logits_host = logits_host.float().contiguous() if logits_host.dtype != torch.float32 else logits_host.contiguous()
+    which = tuple(which)
+    mask = 0
+    for w in which:
+        mask |= L.SCORE_BITS[w]
+    B, Cn = logits_host.shape[0], logits_host.shape[1]
+    spatial = tuple(logits_host.shape[2:])
+    HW = 1
+    for s in spatial:
+        HW *= s
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lib = L.load()
+    nbytes = lib.mss_deeplab_score_host_scratch_bytes(B, Cn, HW, mask)
+    if scratch is None or scratch.numel() < nbytes:
+        scratch = L.workspace(nbytes, dev)
+    if out is None:
+        out = {w: torch.empty((B,) + spatial, dtype=torch.float32, pin_memory=True) for w in which}
+    with torch.cuda.device(dev):
+        rc = lib.mss_deeplab_score_host(logits_host.data_ptr(), B, Cn, HW, mask, L.ptr(out.get("energy")),
+                                        L.ptr(out.get("maxlogit")), L.ptr(out.get("msp")), L.ptr(out.get("entropy")),
+                                        scratch.data_ptr(), scratch.numel(), L.stream_ptr(dev))
+    L.check(rc, "mss_deeplab_score_host")
+    return out

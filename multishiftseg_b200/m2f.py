@@ -1,0 +1,117 @@
+"""Mask2Former post-head inference: drop-ins for ``MaskFormer.semantic_inference``
+(lib/network/mask2former/maskformer_model.py:341-354) and ``TrainM2FOOD.get_anomaly_score``
+(train_m2f.py:387-407), plus the fused entry points that also absorb the ``F.interpolate`` calls of
+``MaskFormer.forward`` (maskformer_model.py:264-277) and the ``sem_seg_postprocess`` crop (:299-300), so
+that the [Q, H, W] mask tensor is never materialised.
+
+All functions take and return CUDA tensors; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+
+__all__ = ["semantic_inference", "get_anomaly_score", "post_head_inference", "anomaly_score_from_lowres"]
+
+
+def _keep_queries(mask_cls: torch.Tensor, num_classes: int):
+    """maskformer_model.py:346-349, evaluated with the same torch ops on the tiny [B, Q, C+1] tensor so the
+    boolean ``keep`` mask is bit-identical: labels != C, score > 0.95, 1 < label < 11."""
+    scores, labels = F.softmax(mask_cls, dim=-1).max(-1)
+    keep = labels.ne(num_classes) & (scores > 0.95) & (labels < 11) & (labels > 1)
+    return scores, keep
+
+
+def _run(cls_logits, mask_logits, padded_size, crop_size, want_semseg, want_anomaly, extra_channels, flags=0):
+    L.require_cuda(cls_logits, "class logits")
+    L.require_cuda(mask_logits, "mask logits")
+    cls_logits = cls_logits.float().contiguous()
+    mask_logits = mask_logits.float().contiguous()
+    B, Q, C1 = cls_logits.shape
+    Cn = C1 - 1
+    Bm, Qm, h, w = mask_logits.shape
+    if (Bm, Qm) != (B, Q):
+        raise ValueError(f"class logits {tuple(cls_logits.shape)} and mask logits {tuple(mask_logits.shape)} disagree")
+    Hp, Wp = int(padded_size[0]), int(padded_size[1])
+    Hc, Wc = min(int(crop_size[0]), Hp), min(int(crop_size[1]), Wp)
+    dev = cls_logits.device
+    lib = L.load()
+    semseg = anomaly = None
+    keep_idx = keep_score = keep_count = None
+    counts: List[int] = [0] * B
+    if want_semseg:
+        if extra_channels:
+            scores, keep = _keep_queries(cls_logits, Cn)
+            counts = keep.sum(-1).tolist()                       # K is data dependent (host sync, as in torch's boolean indexing)
+            # stable order of kept queries: ascending q, exactly scores[keep] / mask_pred[keep]
+            order = torch.argsort((~keep).to(torch.int8), dim=-1, stable=True).to(torch.int32).contiguous()
+            keep_idx, keep_score = order, scores.contiguous()
+            keep_count = keep.sum(-1).to(torch.int32).contiguous()
+        kmax = max(counts) if counts else 0
+        semseg = torch.empty((B, Cn + kmax, Hc, Wc), dtype=torch.float32, device=dev)
+    if want_anomaly:
+        anomaly = torch.empty((B, Hc, Wc), dtype=torch.float32, device=dev)
+    nbytes = lib.mss_m2f_workspace_bytes(B, Q, Cn)
+    ws = L.workspace(nbytes, dev)
+    bstride = semseg.stride(0) if semseg is not None else 0
+    extra_ptr = (semseg.data_ptr() + Cn * Hc * Wc * 4) if (semseg is not None and max(counts) > 0) else 0
+    with torch.cuda.device(dev):
+        rc = lib.mss_m2f_semantic_inference(
+            cls_logits.data_ptr(), mask_logits.data_ptr(), B, Q, Cn, h, w, Hp, Wp, Hc, Wc,
+            L.ptr(semseg), bstride, L.ptr(anomaly), L.ptr(keep_idx) if extra_ptr else 0,
+            L.ptr(keep_score) if extra_ptr else 0, L.ptr(keep_count) if extra_ptr else 0, extra_ptr, bstride,
+            ws.data_ptr(), nbytes, flags, L.stream_ptr(dev))
+    L.check(rc, "mss_m2f_semantic_inference")
+    return semseg, anomaly, counts
+
+
+def semantic_inference(mask_cls: torch.Tensor, mask_pred: torch.Tensor, num_classes: Optional[int] = None) -> torch.Tensor:
+    """maskformer_model.py:341-354 for ONE image: ``mask_cls`` [Q, C+1], ``mask_pred`` [Q, H, W] (already
+    upsampled, as the reference passes it) -> [C + K, H, W]."""
+    if num_classes is not None and num_classes != mask_cls.shape[-1] - 1:
+        raise ValueError("num_classes must equal mask_cls.shape[-1] - 1")
+    H, W = mask_pred.shape[-2:]
+    semseg, _, counts = _run(mask_cls[None], mask_pred[None], (H, W), (H, W), True, False, True)
+    return semseg[0, : mask_cls.shape[-1] - 1 + counts[0]]
+
+
+def get_anomaly_score(other_outputs: Dict[str, torch.Tensor], size: Tuple[int, int]) -> torch.Tensor:
+    """train_m2f.py:387-407: ``other_outputs["pred_masks_ood"]`` is the already-upsampled [B, Q, Hp, Wp]."""
+    cls = other_outputs["pred_logits_ood"]
+    masks = other_outputs["pred_masks_ood"]
+    Hp, Wp = masks.shape[-2:]
+    _, anomaly, _ = _run(cls, masks, (Hp, Wp), size, False, True, False)
+    return anomaly
+
+
+def post_head_inference(pred_logits: torch.Tensor, pred_masks: torch.Tensor, padded_size: Sequence[int],
+                        image_sizes: Optional[Sequence[Sequence[int]]] = None, extra_channels: bool = True,
+                        flags: int = 0) -> List[torch.Tensor]:
+    """maskformer_model.py:264-300 fused: decoder-resolution ``pred_masks`` [B, Q, h, w] -> per image
+    ``sem_seg`` [C + K_b, H_b, W_b] (upsample to ``padded_size``, semantic_inference, crop to the image size)."""
+    B = pred_logits.shape[0]
+    Cn = pred_logits.shape[-1] - 1
+    if image_sizes is None:
+        image_sizes = [tuple(padded_size)] * B
+    sizes = {tuple(int(v) for v in s) for s in image_sizes}
+    if len(sizes) == 1:
+        semseg, _, counts = _run(pred_logits, pred_masks, padded_size, next(iter(sizes)), True, False, extra_channels, flags)
+        return [semseg[b, : Cn + counts[b]] for b in range(B)]
+    out = []
+    for b in range(B):                                            # ragged image sizes: one launch per image
+        s, _, counts = _run(pred_logits[b:b + 1], pred_masks[b:b + 1], padded_size, image_sizes[b], True, False,
+                            extra_channels, flags)
+        out.append(s[0, : Cn + counts[0]])
+    return out
+
+
+def anomaly_score_from_lowres(pred_logits_ood: torch.Tensor, pred_masks_ood: torch.Tensor, padded_size: Sequence[int],
+                              size: Sequence[int], flags: int = 0) -> torch.Tensor:
+    """maskformer_model.py:271-277 + train_m2f.py:387-407 fused: [B, Q, h, w] decoder masks -> [B, H, W] score."""
+    _, anomaly, _ = _run(pred_logits_ood, pred_masks_ood, padded_size, size, False, True, False, flags)
+    return anomaly

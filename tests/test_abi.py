@@ -1,0 +1,77 @@
+"""CPU-side checks of the boundary: the C-ABI library builds, loads and exports exactly what
+include/mss_b200.h declares; the product package contains no route to the oracle or to a CPU fallback."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mss_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"^MSS_API[^;(]*?\b(mss_[a-z0-9_]+)\s*\(", src, flags=re.M)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from multishiftseg_b200 import build
+    return build.build()
+
+
+def test_header_declares_entry_points():
+    syms = declared_symbols()
+    for must in ["mss_deeplab_score", "mss_upsample_bilinear", "mss_m2f_semantic_inference", "mss_ood_metrics",
+                 "mss_sort_pairs", "mss_metrics_tail", "mss_eval_append", "mss_last_error"]:
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in mss_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header(lib_path):
+    from multishiftseg_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    lib = _lib.load()
+    assert lib.mss_abi_version() == 1
+    # pure host-side size queries are callable without a GPU
+    assert lib.mss_sort_pairs_workspace_bytes(1 << 20) > (1 << 20) * 5
+    assert lib.mss_ood_metrics_workspace_bytes(1000) > 0
+    assert lib.mss_tail_workspace_bytes(10) > 0
+    assert lib.mss_m2f_workspace_bytes(2, 100, 19) >= 2 * 100 * 20 * 4
+    assert lib.mss_deeplab_score_host_scratch_bytes(16, 19, 1024 * 2048, 11) > 3 * 19 * 1024 * 2048 * 4
+
+
+def test_only_sm100a_code_in_library(lib_path):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", lib_path], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_product_never_touches_oracle_or_cpu_fallback():
+    pkg = os.path.join(ROOT, "multishiftseg_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                for banned in ("oracle", "sklearn", "scipy", "triton"):
+                    assert not re.search(rf"^\s*(from|import)\s+{banned}\b", src, flags=re.M), (f, banned)
+                assert "torch.compile(" not in src, f
+
+
+def test_missing_cuda_raises_instead_of_falling_back():
+    import numpy as np
+    import torch
+    from multishiftseg_b200 import _lib, deeplab, metric
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.MssError):
+        metric.eval_ood_measure(np.zeros(4, np.float32), np.array([0, 1, 0, 1]))
+    with pytest.raises(_lib.MssError):
+        deeplab.energy_func(torch.zeros(1, 19, 4, 4))

@@ -1,0 +1,212 @@
+"""GPU parity, metric stage: the CUDA path (through the C ABI) must be BIT-IDENTICAL to the reference's
+result -- golden vectors made by running the reference's metric.py, KATs K1-K13, and the C oracle on
+seeded random inputs.  Integer stages (sort, partition, histogram, counts) are compared exactly too."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gen_inputs as gi
+from oracle import c_oracle, metrics_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "metrics_golden.json")))
+
+
+@pytest.fixture(scope="module")
+def M():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device (no fallback)"
+    from multishiftseg_b200 import metric
+    return metric
+
+
+def _unhex(v):
+    return None if v is None else tuple(float.fromhex(x) for x in v)
+
+
+def _tup(r):
+    return None if r is None else tuple(float(x) for x in r)
+
+
+@pytest.mark.parametrize("name", sorted(gi.KATS))
+def test_kats(M, name):
+    s, l = gi.KATS[name]
+    s = np.asarray(s, dtype=np.float32)
+    l = np.asarray(l, dtype=np.int64)
+    gold = GOLD["kats"][name]
+    if isinstance(gold, dict):
+        with pytest.raises(ValueError) as ei:
+            M.eval_ood_measure(s, l)
+        assert str(ei.value) == gold["message"]
+    else:
+        assert _tup(M.eval_ood_measure(s, l)) == _unhex(gold)
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: f"s{c['seed']}-n{c['n']}-{c['mode']}")
+def test_golden_cases(M, case):
+    s, l = gi.metric_case(case["seed"], case["n"], case["mode"], case["p_ood"], case["p_ignore"])
+    assert gi.digest(s, l) == case["sha256"]
+    assert _tup(M.eval_ood_measure(s, l)) == _unhex(case["expected"])
+
+
+def test_image_shaped_cuda_tensors(M):
+    c = GOLD["image_shaped"]
+    s, l = gi.metric_case(c["seed"], int(np.prod(c["shape"])), "cont")
+    st = torch.from_numpy(s).reshape(c["shape"]).cuda()
+    lt = torch.from_numpy(l).reshape(c["shape"]).cuda()
+    assert _tup(M.eval_ood_measure(st, lt)) == _unhex(c["expected"])
+
+
+@pytest.mark.parametrize("ldt", ["uint8", "int32", "int64", "int16"])
+def test_label_dtypes(M, ldt):
+    s, l = gi.metric_case(7, 1000, "q2", label_dtype=ldt)
+    exp = _unhex(next(c for c in GOLD["cases"] if c["seed"] == 7)["expected"])
+    assert _tup(M.eval_ood_measure(s, l)) == exp
+
+
+@pytest.mark.parametrize("n,mode", [(1, "cont"), (2, "cont"), (3, "q0"), (4095, "cont"), (4096, "q2"), (4097, "cont"),
+                                    (8191, "f16"), (65536, "cont"), (1_000_003, "cont"), (1_000_003, "q2"),
+                                    (5_000_011, "cont"), (5_000_011, "f16"), (16_777_216, "cont")])
+def test_random_vs_c_oracle(M, n, mode):
+    s, l = gi.metric_case(1000 + n % 977, n, mode, label_dtype="uint8")
+    exp = c_oracle.eval_ood_measure(s, l)
+    got = _tup(M.eval_ood_measure(s, l))
+    assert got == exp
+
+
+def test_other_ids_and_all_ignored(M):
+    s, l = gi.metric_case(5, 5000, "cont")
+    l2 = np.where(l == 0, 7, np.where(l == 1, 3, l))
+    assert _tup(M.eval_ood_measure(s, l2, train_id_in=7, train_id_out=3)) == c_oracle.eval_ood_measure(s, l)
+    assert M.eval_ood_measure(s, np.full_like(l, 255)) is None
+    assert M.eval_ood_measure(np.zeros(0, np.float32), np.zeros(0, np.int64)) is None
+
+
+def test_nan_in_ignored_pixels_is_fine(M):
+    s, l = gi.metric_case(6, 4000, "cont")
+    exp = c_oracle.eval_ood_measure(s, l)
+    s = s.copy()
+    s[l == 255] = np.nan
+    assert _tup(M.eval_ood_measure(s, l)) == exp
+
+
+def test_float64_scores_rejected(M):
+    with pytest.raises(TypeError):
+        M.eval_ood_measure(np.zeros(4, np.float64), np.array([0, 1, 0, 1]))
+
+
+def test_get_measures_and_fpr(M):
+    s, l = gi.metric_case(8, 20000, "q2")
+    exp = c_oracle.eval_ood_measure(s, l)
+    assert _tup(M.get_measures(s[l == 1], s[l == 0])) == exp
+    assert _tup(M.get_and_print_results(s[l == 1], s[l == 0])) == exp
+    v = l != 255
+    assert float(M.fpr_and_fdr_at_recall(l[v], s[v])) == exp[2]
+    assert float(M.fpr_and_fdr_at_recall(np.where(l[v] == 1, 1, -1), s[v])) == exp[2]
+    with pytest.raises(ValueError):
+        M.fpr_and_fdr_at_recall(l, s)          # {0,1,255}: not binary
+
+
+# ------------------------------------------------------------------------------------ integer stages
+def test_sort_pairs_exact(M):
+    rng = np.random.default_rng(0)
+    for n in [1, 2, 31, 4096, 4097, 100_000, 3_000_001]:
+        k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+        if n > 1000:
+            k[: n // 3] &= np.uint32(0xFF)              # heavy ties / skewed high digits
+        v = rng.integers(0, 2, size=n, dtype=np.uint8)
+        kt = torch.from_numpy(k.view(np.int32)).cuda()
+        vt = torch.from_numpy(v).cuda()
+        M.sort_pairs(kt, vt, n)
+        order = np.argsort(k, kind="stable")
+        assert np.array_equal(kt.cpu().numpy().view(np.uint32), k[order])
+        assert np.array_equal(vt.cpu().numpy(), v[order])       # stable: payload follows input order inside ties
+
+
+def test_counts_and_tail_stage_level(M):
+    s, l = gi.metric_case(11, 300_000, "f16", label_dtype="uint8")
+    tps_ref, fps_ref = mo.ood_counts(s, l)
+    valid = l != 255
+    key = mo.float_key_desc(s[valid])
+    order = np.argsort(key, kind="stable")
+    kt = torch.from_numpy(key[order].view(np.int32)).cuda()
+    vt = torch.from_numpy((l[valid] == 1).astype(np.uint8)[order]).cuda()
+    tps, fps, npos, nneg = M.counts_from_sorted(kt, vt, kt.numel())
+    assert np.array_equal(tps.cpu().numpy(), tps_ref) and np.array_equal(fps.cpu().numpy(), fps_ref)
+    assert (npos, nneg) == (int(tps_ref[-1]), int(fps_ref[-1]))
+    # offsets (the multi-GPU path): global prefixes are added exactly
+    tps2, fps2, _, _ = M.counts_from_sorted(kt, vt, kt.numel(), pos_before=10, idx_before=100)
+    assert np.array_equal(tps2.cpu().numpy(), tps_ref + 10) and np.array_equal(fps2.cpu().numpy(), fps_ref + 90)
+    res, t_roc = M.metrics_tail(tps, fps)
+    assert _tup(res) == c_oracle.metrics_from_counts(tps_ref, fps_ref)
+
+
+def test_histogram_and_partition(M):
+    from multishiftseg_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(3)
+    n = 1_234_567
+    k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    v = rng.integers(0, 2, size=n, dtype=np.uint8)
+    kt = torch.from_numpy(k.view(np.int32)).cuda()
+    vt = torch.from_numpy(v).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    hist = torch.empty(1 << 16, dtype=torch.int64, device="cuda")
+    assert lib.mss_keys_histogram(kt.data_ptr(), n, 16, hist.data_ptr(), st) == 0
+    assert np.array_equal(hist.cpu().numpy(), np.bincount(k >> 16, minlength=1 << 16))
+    spl = np.array([1 << 30, 1 << 31, 3 << 30], dtype=np.uint32)
+    splt = torch.from_numpy(spl.view(np.int32)).cuda()
+    ko, vo = torch.empty_like(kt), torch.empty_like(vt)
+    nb = lib.mss_partition_workspace_bytes(n)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    counts = (C.c_int64 * 4)()
+    assert lib.mss_partition_pairs(kt.data_ptr(), vt.data_ptr(), n, splt.data_ptr(), 4, ko.data_ptr(), vo.data_ptr(),
+                                   counts, ws.data_ptr(), nb, st) == 0
+    dest = np.searchsorted(spl, k, side="right")
+    order = np.argsort(dest, kind="stable")
+    assert list(counts) == np.bincount(dest, minlength=4).tolist()
+    assert np.array_equal(ko.cpu().numpy().view(np.uint32), k[order])
+    assert np.array_equal(vo.cpu().numpy(), v[order])
+
+
+def test_one_shot_c_entry(M):
+    from multishiftseg_b200 import _lib as L
+    lib = L.load()
+    s, l = gi.metric_case(12, 777_777, "cont", label_dtype="int64")
+    st_, lt = torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda()
+    nb = lib.mss_ood_metrics_workspace_bytes(s.size)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    out, cnt = (C.c_double * 3)(), (C.c_int64 * 4)()
+    rc = lib.mss_ood_metrics(st_.data_ptr(), lt.data_ptr(), L.LABEL_I64, s.size, 0, 1, ws.data_ptr(), nb, out, cnt,
+                             torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, L.last_error()
+    exp, counts = c_oracle.eval_ood_measure(s, l, return_counts=True)
+    assert tuple(out) == exp
+    assert list(cnt) == counts.tolist()
+    # empty class -> MSS_EMPTY_CLASS (reference: None)
+    lt0 = torch.zeros_like(lt)
+    assert lib.mss_ood_metrics(st_.data_ptr(), lt0.data_ptr(), L.LABEL_I64, s.size, 0, 1, ws.data_ptr(), nb, out, cnt,
+                               torch.cuda.current_stream().cuda_stream) == L.MSS_EMPTY_CLASS
+
+
+def test_idempotent_and_permutation_invariant(M):
+    """size-independent properties at a BASELINE-sized image batch (4 x 1024 x 2048)."""
+    n = 4 * 1024 * 2048
+    g = torch.Generator(device="cuda").manual_seed(5)
+    s = torch.randn(n, device="cuda", generator=g)
+    lab = torch.where(torch.rand(n, device="cuda", generator=g) < 0.05, 1, 0).to(torch.uint8)
+    lab[torch.rand(n, device="cuda", generator=g) > 0.95] = 255
+    s = s + (lab == 1) * 1.5
+    r1 = _tup(M.eval_ood_measure(s, lab))
+    r2 = _tup(M.eval_ood_measure(s, lab))
+    perm = torch.randperm(n, device="cuda", generator=g)
+    r3 = _tup(M.eval_ood_measure(s[perm], lab[perm]))
+    assert r1 == r2 == r3
+    # monotone transform of the scores leaves all three metrics unchanged
+    r4 = _tup(M.eval_ood_measure(s * 2.0, lab))
+    assert r4 == r1
+    assert r1 == c_oracle.eval_ood_measure(s.cpu().numpy(), lab.cpu().numpy())
