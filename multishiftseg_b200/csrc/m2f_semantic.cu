@@ -10,7 +10,7 @@
 // Fast path (exact x4 upsample, the model's only configuration: common stride 4, anomaly_ft.yaml:30):
 //   CTA = 256 threads = 32 x 8, output tile 128 x 16 px, thread = 2 rows x 4 cols (8 px, 152 fp32
 //   accumulators).  The 6 x 34 low-res patch of every query is staged by TMA (cp.async.bulk.tensor.3d,
-//   box 36 x 6 x QCHUNK, zero fill outside the image, indices clamped at read time to reproduce
+//   box 40 x 6 x QCHUNK (16-byte aligned start), zero fill outside the image, indices clamped at read time to reproduce
 //   torch's edge replication) through a 3-stage mbarrier ring.  Per query and thread: 6 LDS, 16 lerp
 //   ops, 8 sigmoids (ex2.approx + rcp.approx), 152 FFMA.  Bound: FP32 FMA pipe, not HBM.
 // Generic path: any resize factor (incl. identity = masks already upsampled), any C <= 32.
@@ -25,7 +25,9 @@ constexpr int M2F_CP = 20;         // padded row of the class-probability table 
 constexpr int M2F_MAXQ = 128;
 constexpr int QCHUNK = 20;         // queries per TMA stage
 constexpr int STAGES = 3;
-constexpr int BOX_W = 36, BOX_H = 6;   // low-res patch: 34 x 6 used, inner extent padded to 16 B
+constexpr int BOX_W = 40, BOX_H = 6;   // low-res patch: cols -4..35 of the tile (34 used): the box must START on a
+                                        // 16-byte boundary in global memory (x0 % 4 == 0) or UTMALDG faults
+constexpr int BOX_X0 = 4;              // tile column origin = 32*bx - BOX_X0
 constexpr int TILE_W = 128, TILE_H = 16;
 constexpr int STAGE_FLOATS = QCHUNK * BOX_H * BOX_W;
 constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(256, 1)
 m2f_fused_x4_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ probs, int Q, int h, int w,
                     M2FOut out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *s_tile = reinterpret_cast<float *>(smem_raw);                               // [STAGES][QCHUNK][6][36]
+    float *s_tile = reinterpret_cast<float *>(smem_raw);                               // [STAGES][QCHUNK][6][40]
     float *s_probs = s_tile + STAGES * STAGE_FLOATS;                                   // [Q][20]
     int *s_keep = reinterpret_cast<int *>(s_probs + M2F_MAXQ * M2F_CP);                // [Q]
     float *s_kscore = reinterpret_cast<float *>(s_keep + M2F_MAXQ);                    // [Q]
@@ -111,7 +113,7 @@ m2f_fused_x4_kernel(const __grid_constant__ CUtensorMap tmap, const float *__res
 
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int b = blockIdx.z;
-    const int sx0 = blockIdx.x * (TILE_W / 4) - 1, sy0 = blockIdx.y * (TILE_H / 4) - 1;
+    const int sx0 = blockIdx.x * (TILE_W / 4) - BOX_X0, sy0 = blockIdx.y * (TILE_H / 4) - 1;
     const int n_chunks = (Q + QCHUNK - 1) / QCHUNK;
 
     if (tid == 0) {
