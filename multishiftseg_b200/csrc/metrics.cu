@@ -268,11 +268,21 @@ fpr_partial_kernel(const long long *__restrict__ tps, long long T, double P, dou
     }
 }
 
-__global__ void fpr_final_kernel(const Best *__restrict__ partial, int n, const long long *__restrict__ fps,
-                                 double N, double *__restrict__ out, long long *__restrict__ kout) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        Best b = partial[0];
-        for (int i = 1; i < n; i++) b = better(b, partial[i]);
+__global__ void __launch_bounds__(256)
+fpr_final_kernel(const Best *__restrict__ partial, int n, const long long *__restrict__ fps, double N,
+                 double *__restrict__ out, long long *__restrict__ kout) {
+    Best b{INFINITY, -1};
+    for (int i = threadIdx.x; i < n; i += 256) b = better(b, partial[i]);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        Best o{__shfl_xor_sync(0xffffffffu, b.d, s), __shfl_xor_sync(0xffffffffu, b.k, s)};
+        b = better(b, o);
+    }
+    __shared__ Best sb[8];
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) b = better(b, sb[w]);
         out[0] = __ddiv_rn((double)fps[b.k], N);
         kout[0] = b.k;
     }
@@ -430,7 +440,7 @@ extern "C" int mss_metrics_tail(const int64_t *tps_, const int64_t *fps_, int64_
     int fgrid = (int)std::min<long long>((T + 255) / 256, 1024);
     fpr_partial_kernel<<<fgrid, 256, 0, st>>>(tps, T, P, recall_level, partial);
     MSS_CHECK_LAUNCH();
-    fpr_final_kernel<<<1, 32, 0, st>>>(partial, fgrid, fps, N, fpr_out, fpr_k);
+    fpr_final_kernel<<<1, 256, 0, st>>>(partial, fgrid, fps, N, fpr_out, fpr_k);
     MSS_CHECK_LAUNCH();
     std::vector<double> h_ap((size_t)n_ap), h_roc((size_t)n_roc);
     double h_fpr = 0.0;

@@ -41,9 +41,26 @@ struct SplitterDigit {
     }
 };
 
+// Lanes holding the same BITS-bit value as this lane, from BITS ballots.  (match.any does the same in one
+// instruction but costs ~200 cycles per warp on sm_100 when the 32 values are distinct -- measured with
+// ncu in round 1: it made the histogram 9x and the scatter pass 2x slower than this form.)
+template <int BITS>
+__device__ __forceinline__ unsigned match_bits(unsigned d, bool valid) {
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+    if (!valid) peers = ~peers;                  // lanes past the end group among themselves
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
 // ---- upfront histogram of the four digits ------------------------------------------------------------
-// Upper digits of real score distributions are extremely skewed (sign + exponent bits), so shared
-// atomics would serialise 32-way; match.any aggregates equal digits inside the warp first.
+// Digits of real score distributions are extremely skewed (sign/exponent bits; zeroed mantissa bits of
+// fp16-born scores), so plain shared atomics would serialise up to 32-way: equal digits are aggregated
+// inside the warp first and only the lowest lane of each group issues one atomic.
 __global__ void __launch_bounds__(512)
 radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned long long *__restrict__ hist) {
     __shared__ unsigned s_hist[4][RADIX];
@@ -56,14 +73,11 @@ radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned 
     for (long long it = 0; it < iters; it++, i += stride) {
         const bool valid = i < n;
         const uint32_t k = valid ? __ldg(keys + i) : 0u;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const unsigned d = (k >> (8 * p)) & 255u;
-                const unsigned peers = __match_any_sync(act, d);
-                if ((peers & lt) == 0) atomicAdd(&s_hist[p][d], __popc(peers));
-            }
+        for (int p = 0; p < 4; p++) {
+            const unsigned d = (k >> (8 * p)) & 255u;
+            const unsigned peers = match_bits<8>(d, valid);
+            if (valid && (peers & lt) == 0) atomicAdd(&s_hist[p][d], __popc(peers));
         }
     }
     __syncthreads();
@@ -154,21 +168,29 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict_
 
     uint8_t val[SORT_IPT];
     unsigned short rank[SORT_IPT];
+    unsigned peers[SORT_IPT];
     const unsigned lt = lanemask_lt();
+    // phase 1 (independent, pipelined): who in my warp holds the same digit as item i
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
         const int idx = wbase + i * 32;
         const bool valid = idx < tile_n;
         val[i] = s_vals[idx];
-        const unsigned d = valid ? digit_of(key[i]) : RADIX;   // invalid lanes form their own group
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const unsigned below = __popc(peers & lt);
+        peers[i] = match_bits<8>(valid ? digit_of(key[i]) : 0u, valid);
+    }
+    // phase 2 (serial per warp, item order == memory order => stable): running per-digit counters
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        const int idx = wbase + i * 32;
+        const bool valid = idx < tile_n;
+        const unsigned below = __popc(peers[i] & lt);
         unsigned old = 0;
         if (below == 0 && valid) {
+            const unsigned d = digit_of(key[i]);
             old = s_warp_hist[warp][d];
-            s_warp_hist[warp][d] = old + __popc(peers);
+            s_warp_hist[warp][d] = old + __popc(peers[i]);
         }
-        old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+        old = __shfl_sync(0xffffffffu, old, __ffs(peers[i]) - 1);
         rank[i] = (unsigned short)(old + below);
         __syncwarp();
     }
@@ -252,15 +274,20 @@ keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift,
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long iters = (n + stride - 1) / stride;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lt = lanemask_lt();
+    const unsigned lane = lane_id();
     for (long long it = 0; it < iters; it++, i += stride) {
         const bool valid = i < n;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned b = __ldg(keys + i) >> shift;
-            const unsigned peers = __match_any_sync(act, b);
-            if ((peers & lt) == 0) atomicAdd(hist + b, (unsigned long long)__popc(peers));
+        const unsigned b = valid ? (__ldg(keys + i) >> shift) : 0u;
+        unsigned remaining = __ballot_sync(0xffffffffu, valid);
+        // peel groups of equal bins (leader = lowest remaining lane); after 4 rounds fall back to plain atomics
+        for (int round = 0; round < 4 && remaining; round++) {
+            const int leader = __ffs(remaining) - 1;
+            const unsigned v = __shfl_sync(0xffffffffu, b, leader);
+            const unsigned m = __ballot_sync(0xffffffffu, valid && b == v) & remaining;
+            if ((int)lane == leader) atomicAdd(hist + v, (unsigned long long)__popc(m));
+            remaining &= ~m;
         }
+        if ((remaining >> lane) & 1u) atomicAdd(hist + b, 1ull);
     }
 }
 
