@@ -21,6 +21,7 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096
 constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int LB_WINDOW = 8;                        // look-back statuses fetched per round trip
 
 struct ShiftDigit {
     int shift;
@@ -120,78 +121,85 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <typename DigitFn>
-__global__ void __launch_bounds__(SORT_THREADS, 3)
-onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out,
-                     const uint8_t *__restrict__ vals_in, uint8_t *__restrict__ vals_out, long long n,
-                     const unsigned long long *__restrict__ bin_base, unsigned long long *tile_status,
-                     unsigned *tile_counter, DigitFn digit_of) {
-    __shared__ __align__(16) uint32_t s_keys[SORT_TILE];
-    __shared__ __align__(16) uint8_t s_vals[SORT_TILE];
-    __shared__ unsigned s_warp_hist[SORT_WARPS][RADIX];
-    __shared__ unsigned s_tile_start[RADIX];
-    __shared__ unsigned long long s_global[RADIX];
-    __shared__ unsigned s_scan[SORT_WARPS];
-    __shared__ unsigned s_tile;
-
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+// 8-bit match for a tile without padding lanes: 4 instructions per bit (predicate, ballot, select, and)
+__device__ __forceinline__ unsigned match8_full(unsigned d) {
+    unsigned peers = 0xffffffffu;
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) s_warp_hist[w][tid] = 0;
-    __syncthreads();
-    const unsigned tile = s_tile;
+    for (int b = 0; b < 8; b++) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
+struct SweepSmem {
+    __align__(16) uint32_t keys[SORT_TILE];
+    __align__(16) uint8_t vals[SORT_TILE];
+    unsigned warp_hist[SORT_WARPS][RADIX];   // per-warp digit counts -> exclusive scatter bases
+    unsigned long long global[RADIX];        // global output index of tile-sorted position 0 of each digit
+    unsigned scan[SORT_WARPS];
+    unsigned tile;
+};
+
+// FULL: the tile holds exactly SORT_TILE pairs (every tile but possibly the last): no bounds predicates.
+template <typename DigitFn, bool FULL>
+__device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__restrict__ keys_in,
+                                           uint32_t *__restrict__ keys_out, const uint8_t *__restrict__ vals_in,
+                                           uint8_t *__restrict__ vals_out, long long n,
+                                           const unsigned long long *__restrict__ bin_base,
+                                           unsigned long long *tile_status, DigitFn digit_of, unsigned tile) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long tile_base = (long long)tile * SORT_TILE;
-    const int tile_n = (int)min((long long)SORT_TILE, n - tile_base);
+    const int tile_n = FULL ? SORT_TILE : (int)(n - tile_base);
 
     // labels of the tile: one coalesced 16-byte load per thread, staged in smem
     {
         const long long b = tile_base + (long long)tid * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (b + 16 <= n && ((((uintptr_t)vals_in) & 15) == 0)) {
+        if ((FULL || b + 16 <= n) && ((((uintptr_t)vals_in) & 15) == 0)) {
             v = *reinterpret_cast<const uint4 *>(vals_in + b);
         } else {
             uint8_t *pv = reinterpret_cast<uint8_t *>(&v);
             for (int j = 0; j < 16; j++) pv[j] = (b + j < n) ? vals_in[b + j] : 0;
         }
-        *reinterpret_cast<uint4 *>(s_vals + tid * 16) = v;
+        *reinterpret_cast<uint4 *>(sm.vals + tid * 16) = v;
     }
-
     // keys, warp-striped: item i of lane l in warp w sits at w*512 + i*32 + l
     uint32_t key[SORT_IPT];
     const int wbase = warp * (32 * SORT_IPT) + lane;
+    const uint32_t *kp = keys_in + tile_base + wbase;
 #pragma unroll
-    for (int i = 0; i < SORT_IPT; i++) {
-        const int idx = wbase + i * 32;
-        key[i] = (idx < tile_n) ? __ldg(keys_in + tile_base + idx) : 0u;
-    }
-    __syncthreads();   // s_vals staged, s_warp_hist zeroed
+    for (int i = 0; i < SORT_IPT; i++) key[i] = (FULL || wbase + i * 32 < tile_n) ? __ldg(kp + i * 32) : 0u;
+    __syncthreads();   // vals staged, warp_hist zeroed (by the caller)
 
-    uint8_t val[SORT_IPT];
-    unsigned short rank[SORT_IPT];
+    // phase 1 (independent, pipelined): lanes of my warp holding the same digit as my item i
     unsigned peers[SORT_IPT];
-    const unsigned lt = lanemask_lt();
-    // phase 1 (independent, pipelined): who in my warp holds the same digit as item i
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
-        const int idx = wbase + i * 32;
-        const bool valid = idx < tile_n;
-        val[i] = s_vals[idx];
-        peers[i] = match_bits<8>(valid ? digit_of(key[i]) : 0u, valid);
+        if (FULL) peers[i] = match8_full(digit_of(key[i]));
+        else {
+            const bool valid = wbase + i * 32 < tile_n;
+            peers[i] = match_bits<8>(valid ? digit_of(key[i]) : 0u, valid);
+        }
     }
-    // phase 2 (serial per warp, item order == memory order => stable): running per-digit counters
+    // phase 2 (serial per warp; item order == memory order, hence stable): running per-digit counters.
+    // rank[i] bit 15 carries the label so it needs no register of its own.
+    unsigned short rank[SORT_IPT];
+    const unsigned lt = lanemask_lt();
+    unsigned *wh = sm.warp_hist[warp];
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
-        const int idx = wbase + i * 32;
-        const bool valid = idx < tile_n;
+        const bool valid = FULL || (wbase + i * 32 < tile_n);
         const unsigned below = __popc(peers[i] & lt);
         unsigned old = 0;
         if (below == 0 && valid) {
             const unsigned d = digit_of(key[i]);
-            old = s_warp_hist[warp][d];
-            s_warp_hist[warp][d] = old + __popc(peers[i]);
+            old = wh[d];
+            wh[d] = old + __popc(peers[i]);
         }
         old = __shfl_sync(0xffffffffu, old, __ffs(peers[i]) - 1);
-        rank[i] = (unsigned short)(old + below);
+        rank[i] = (unsigned short)((old + below) | ((unsigned)sm.vals[wbase + i * 32] << 15));
         __syncwarp();
     }
     __syncthreads();
@@ -199,57 +207,64 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict_
     // thread d: prefix over the 8 warps for digit d, tile count, publish, look back
     {
         const unsigned d = tid;
-        unsigned tot = 0;
+        unsigned cnt[SORT_WARPS], tot = 0;
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) {
-            unsigned c = s_warp_hist[w][d];
-            s_warp_hist[w][d] = tot;
-            tot += c;
-        }
+        for (int w = 0; w < SORT_WARPS; w++) { cnt[w] = sm.warp_hist[w][d]; tot += cnt[w]; }
         unsigned long long *my = tile_status + (size_t)tile * RADIX + d;
-        if (tile == 0) st_status(my, FLAG_INC | tot);
-        else st_status(my, FLAG_AGG | tot);
+        st_status(my, (tile == 0 ? FLAG_INC : FLAG_AGG) | tot);
 
-        // exclusive scan of tot over the 256 digits
+        // exclusive scan of tot over the 256 digits -> first tile-sorted position of digit d
         unsigned inc = tot;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
             unsigned t = __shfl_up_sync(0xffffffffu, inc, s);
             if (lane >= s) inc += t;
         }
-        if (lane == 31) s_scan[warp] = inc;
+        if (lane == 31) sm.scan[warp] = inc;
         __syncthreads();
-        unsigned wsum = 0;
+        unsigned start = inc - tot;
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) wsum += (w < (int)warp) ? s_scan[w] : 0u;
-        const unsigned start = wsum + inc - tot;
-        s_tile_start[d] = start;
+        for (int w = 0; w < SORT_WARPS; w++) start += (w < (int)warp) ? sm.scan[w] : 0u;
+        // scatter base of (warp w, digit d) = start + counts of the warps before w
+        unsigned run = start;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) { sm.warp_hist[w][d] = run; run += cnt[w]; }
 
+        // Decoupled look-back, LB_WINDOW predecessors per round trip (the loads of one window are
+        // independent, so they overlap; a lock-step wave of tiles walks back over hundreds of them).
         unsigned long long prefix = 0;
         if (tile > 0) {
             long long t = (long long)tile - 1;
-            while (true) {
-                unsigned long long st = ld_status(tile_status + (size_t)t * RADIX + d);
-                if ((st >> 62) == 0) continue;           // predecessor not published yet
-                prefix += st & VAL_MASK;
-                if ((st >> 62) == 2) break;
-                t--;
+            bool done = false;
+            while (!done) {
+                unsigned long long st[LB_WINDOW];
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++)
+                    st[j] = (t - j >= 0) ? ld_status(tile_status + (size_t)(t - j) * RADIX + d) : FLAG_INC;
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++) {
+                    if (!done) {
+                        unsigned long long v = st[j];
+                        while ((v >> 62) == 0) v = ld_status(tile_status + (size_t)(t - j) * RADIX + d);
+                        prefix += v & VAL_MASK;
+                        done = (v >> 62) == 2;
+                    }
+                }
+                t -= LB_WINDOW;
             }
             st_status(my, FLAG_INC | (prefix + tot));
         }
-        s_global[d] = bin_base[d] + prefix - start;
+        sm.global[d] = bin_base[d] + prefix - start;
     }
     __syncthreads();
 
-    // scatter into tile-sorted order in smem
+    // scatter into tile-sorted order in smem (labels were all read in phase 2, so vals can be overwritten)
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
-        const int idx = wbase + i * 32;
-        if (idx < tile_n) {
-            const unsigned d = digit_of(key[i]);
-            const unsigned pos = s_tile_start[d] + s_warp_hist[warp][d] + rank[i];
-            s_keys[pos] = key[i];
-            s_vals[pos] = val[i];   // safe: every s_vals read happened before the last __syncthreads
+        if (FULL || wbase + i * 32 < tile_n) {
+            const unsigned pos = wh[digit_of(key[i])] + (rank[i] & 0x7fffu);
+            sm.keys[pos] = key[i];
+            sm.vals[pos] = (uint8_t)(rank[i] >> 15);
         }
     }
     __syncthreads();
@@ -258,13 +273,32 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict_
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
         const int p = i * SORT_THREADS + tid;
-        if (p < tile_n) {
-            const uint32_t k = s_keys[p];
-            const unsigned long long o = s_global[digit_of(k)] + p;
+        if (FULL || p < tile_n) {
+            const uint32_t k = sm.keys[p];
+            const unsigned long long o = sm.global[digit_of(k)] + p;
             keys_out[o] = k;
-            vals_out[o] = s_vals[p];
+            vals_out[o] = sm.vals[p];
         }
     }
+}
+
+template <typename DigitFn>
+__global__ void __launch_bounds__(SORT_THREADS, 3)
+onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out,
+                     const uint8_t *__restrict__ vals_in, uint8_t *__restrict__ vals_out, long long n,
+                     const unsigned long long *__restrict__ bin_base, unsigned long long *tile_status,
+                     unsigned *tile_counter, DigitFn digit_of) {
+    __shared__ SweepSmem sm;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);   // tiles are numbered in start order: the
+#pragma unroll                                           // look-back only waits on tiles already running
+    for (int w = 0; w < SORT_WARPS; w++) sm.warp_hist[w][tid] = 0;
+    __syncthreads();
+    const unsigned tile = sm.tile;
+    if ((long long)(tile + 1) * SORT_TILE <= n)
+        sweep_tile<DigitFn, true>(sm, keys_in, keys_out, vals_in, vals_out, n, bin_base, tile_status, digit_of, tile);
+    else
+        sweep_tile<DigitFn, false>(sm, keys_in, keys_out, vals_in, vals_out, n, bin_base, tile_status, digit_of, tile);
 }
 
 // top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536, global atomics after

@@ -1,0 +1,112 @@
+"""Host / collective logic of the multi-GPU evaluator under gloo (world_size 2 and 3, CPU): the local compute
+steps are served by the oracle-backed NumpyBackend, everything else (splitters, all_to_all plan, prefix
+bookkeeping, gather + tail) is the product code.  The distributed result must be bit-identical to the
+single-process result and to the reference-pinned oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import gen_inputs as gi
+from multishiftseg_b200.evaluator import StreamingEvaluator, choose_splitters
+from numpy_backend import NumpyBackend
+from oracle import c_oracle
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+CASES = [("cont", 20011, 0.1, 0.05), ("q2", 30007, 0.05, 0.2), ("const", 5000, 0.3, 0.0), ("f16", 40009, 0.01, 0.05),
+         ("zeros", 9000, 0.3, 0.05)]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = []
+    for ci, (mode, n, p_ood, p_ign) in enumerate(CASES):
+        s, l = gi.metric_case(100 + ci, n, mode, p_ood, p_ign)
+        ev = StreamingEvaluator(n, backend=NumpyBackend(), distributed=True)
+        # images sharded round-robin in chunks ("images") of 1000 pixels, two updates per rank
+        chunks = [(i, min(i + 1000, n)) for i in range(0, n, 1000)]
+        mine = chunks[rank::world]
+        for a, b in mine:
+            ev.update(s[a:b], l[a:b])
+        r = ev.compute()
+        out.append(None if r is None else tuple(float(v) for v in r))
+    # a rank with no data at all, and an all-ignored dataset
+    ev = StreamingEvaluator(10, backend=NumpyBackend(), distributed=True)
+    if rank == 0:
+        ev.update(np.array([.1, .4, .35, .8], np.float32), np.array([0, 0, 1, 1]))
+    r = ev.compute()
+    out.append(tuple(float(v) for v in r))
+    ev = StreamingEvaluator(10, backend=NumpyBackend(), distributed=True)
+    ev.update(np.array([.1, .4], np.float32), np.array([255, 0]))
+    out.append(ev.compute())
+    # NaN on one rank raises on every rank
+    ev = StreamingEvaluator(10, backend=NumpyBackend(), distributed=True)
+    ev.update(np.array([.1, np.nan if rank == world - 1 else .2, .3], np.float32), np.array([0, 1, 1]))
+    try:
+        ev.compute()
+        out.append("no error")
+    except ValueError as e:
+        out.append(str(e))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_equals_single_process_and_oracle(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = []
+    for ci, (mode, n, p_ood, p_ign) in enumerate(CASES):
+        s, l = gi.metric_case(100 + ci, n, mode, p_ood, p_ign)
+        want.append(c_oracle.eval_ood_measure(s, l))
+        single = StreamingEvaluator(n, backend=NumpyBackend(), distributed=False)
+        single.update(s, l)
+        assert tuple(float(v) for v in single.compute()) == want[-1]
+    want.append((0.75, float.fromhex("0x1.aaaaaaaaaaaaap-1"), 0.5))     # K1
+    want.append(None)
+    want.append("Input contains NaN.")
+    for r in range(world):
+        assert results[r] == want, (r, results[r], want)
+
+
+def test_choose_splitters_properties():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 4, 8):
+        hist = rng.integers(0, 1000, size=1 << 16)
+        hist[rng.integers(0, 1 << 16, size=60000)] = 0
+        spl = choose_splitters(hist, world)
+        assert len(spl) == world - 1 and spl == sorted(spl)
+        assert all(s % (1 << 16) == 0 or s == 0xFFFFFFFF for s in spl)
+        # balance: every rank gets at most its share plus one bin
+        bounds = [0] + [s >> 16 for s in spl] + [1 << 16]
+        loads = [int(hist[a:b].sum()) for a, b in zip(bounds[:-1], bounds[1:])]
+        assert sum(loads) == int(hist.sum())
+        assert max(loads) <= int(hist.sum()) / world + int(hist.max()) + 1
+    # degenerate: everything in one bin -> one rank takes it all, still a valid ascending split
+    hist = np.zeros(1 << 16, np.int64)
+    hist[12345] = 10 ** 9
+    spl = choose_splitters(hist, 4)
+    assert spl == sorted(spl)
