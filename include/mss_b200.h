@@ -129,7 +129,8 @@ MSS_API int mss_deeplab_anomaly_score(const float *ood_logits, int64_t B, int C,
  * TMA-staged x4 kernel (testing).  Limits: Q <= 128, C <= 32; the fast path needs C == 19, Hp == 4h,
  * Wp == 4w, w % 4 == 0 (always true for the model: stride 4, size divisibility 32).
  * ------------------------------------------------------------------------------------------- */
-#define MSS_M2F_FORCE_GENERIC 1u
+#define MSS_M2F_FORCE_GENERIC 1u   /* any-resize kernel (no TMA) */
+#define MSS_M2F_FORCE_FFMA 2u      /* TMA-staged x4 kernel with the FP32-FMA contraction instead of the 3xTF32 tensor-core one */
 MSS_API size_t mss_m2f_workspace_bytes(int64_t B, int Q, int C);
 MSS_API int mss_m2f_semantic_inference(const float *cls_logits, const float *mask_logits,
                                int64_t B, int Q, int C, int h, int w, int Hp, int Wp, int Hc, int Wc,

@@ -16,6 +16,16 @@ struct ScoreOut {
     float *energy, *maxlogit, *msp, *entropy;
 };
 
+// exp(d) for d <= 0 (d = x - max): ex2.approx on the pre-scaled argument.  Relative error is 2^-22 from
+// ex2.approx plus |d| * 6e-8 from rounding d*log2(e); terms with large |d| are negligible in the sum, so the
+// sum's relative error stays ~1e-7 -- well inside the 1e-5 bar -- at 2 instructions instead of ~9 per class
+// (ncu, round 1: the accurate expf kept issue utilisation at 72 % and capped the kernel at 84 % of HBM peak).
+__device__ __forceinline__ float exp_neg(float d) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(d * 1.4426950408889634f));
+    return e;
+}
+
 template <bool ENTROPY>
 __device__ __forceinline__ void finish_pixel(float m, float s, float t, float &energy, float &maxlogit,
                                              float &msp, float &entropy, float msafe) {
@@ -63,7 +73,7 @@ deeplab_score_vec4_kernel(const float *__restrict__ logits, long long HW, long l
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 float dx = x[c].x - ms.x, dy = x[c].y - ms.y, dz = x[c].z - ms.z, dw = x[c].w - ms.w;
-                float ex = expf(dx), ey = expf(dy), ez = expf(dz), ew = expf(dw);
+                float ex = exp_neg(dx), ey = exp_neg(dy), ez = exp_neg(dz), ew = exp_neg(dw);
                 s.x += ex; s.y += ey; s.z += ez; s.w += ew;
                 if (ENTROPY) {
                     // 0 * -inf guard: a -inf logit contributes p log p = 0
