@@ -190,6 +190,15 @@ MSS_API int mss_metrics_tail(const int64_t *tps, const int64_t *fps, int64_t T, 
                      void *workspace, size_t workspace_bytes, double out_host[3], int64_t *T_roc_host,
                      void *stream);
 
+/* host-only helper (no device work): numpy's pairwise-summation tree (np.add.reduce over float64, leaves of
+ * <= 128 terms, split at n/2 rounded down to a multiple of 8) that mss_metrics_tail replays for the AUROC /
+ * AP sums of sklearn (_ranking.py auc / average_precision_score).  Returns leaf `leaf`'s [start, start+len)
+ * and the number of leaves, computed by the same table descent the device kernels use. */
+MSS_API int mss_pairwise_leaf_bounds(int64_t n, int64_t leaf, int64_t *start_host, int64_t *len_host,
+                             int64_t *n_leaves_host);
+/* host-only: np.sum(terms) over float64 through the same plan / descent / combine code (test hook) */
+MSS_API int mss_pairwise_sum_host(const double *terms_host, int64_t n, double *out_host);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points: what a reference-side caller holding numpy / CPU tensors would call.
  * Inputs and outputs are HOST pointers (pinned memory recommended); the library stages them

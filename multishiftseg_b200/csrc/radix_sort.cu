@@ -59,33 +59,90 @@ __device__ __forceinline__ unsigned match_bits(unsigned d, bool valid) {
 }
 
 // ---- upfront histogram of the four digits ------------------------------------------------------------
-// Digits of real score distributions are extremely skewed (sign/exponent bits; zeroed mantissa bits of
-// fp16-born scores), so plain shared atomics would serialise up to 32-way: equal digits are aggregated
-// inside the warp first and only the lowest lane of each group issues one atomic.
-__global__ void __launch_bounds__(512)
-radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned long long *__restrict__ hist) {
-    __shared__ unsigned s_hist[4][RADIX];
-    for (int i = threadIdx.x; i < 4 * RADIX; i += blockDim.x) (&s_hist[0][0])[i] = 0;
-    __syncthreads();
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long iters = (n + stride - 1) / stride;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lt = lanemask_lt();
-    for (long long it = 0; it < iters; it++, i += stride) {
-        const bool valid = i < n;
-        const uint32_t k = valid ? __ldg(keys + i) : 0u;
+// Shared-memory atomics cost ~1-2 cycles per LANE on sm_100 (ncu, round 1: the warp-aggregated atomic
+// version of this kernel took 436 us for 32 M keys, 20x its HBM time), and the digits of real score
+// distributions are extremely skewed (sign/exponent bits; zeroed mantissa bits of fp16-born scores), so
+// contention-sensitive schemes are out.  Instead every thread owns a PRIVATE set of 8-bit counters,
+// 4 digits x 256 bins, updated with plain byte load / add / byte store: no atomics, no dependence on the
+// key distribution.  Counter (digit d, bin b) of thread (warp w, lane l) lives at byte
+//     d*32768 + b*128 + l*4 + w
+// so a warp's 32 accesses always fall into 32 different banks whatever the bins are.  A thread handles at
+// most 252 keys between two flushes (8-bit counters cannot overflow); a flush sums each 128-byte row
+// (= the 128 threads' counters of one bin) with dp4a into per-thread 32-bit running totals.
+constexpr int HIST_THREADS = 128;
+constexpr int HIST_ROWS = 4 * RADIX;                       // (digit, bin) rows of 128 bytes
+constexpr int HIST_SMEM = HIST_ROWS * HIST_THREADS;        // 131072 bytes
+constexpr int HIST_ITERS_PER_FLUSH = 63;                   // x 4 keys per thread per iteration = 252
+constexpr int HIST_ROWS_PER_THREAD = HIST_ROWS / HIST_THREADS;   // 8
+
+__device__ __forceinline__ void hist_bump(unsigned char *cnt, uint32_t key) {
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const unsigned d = (k >> (8 * p)) & 255u;
-            const unsigned peers = match_bits<8>(d, valid);
-            if (valid && (peers & lt) == 0) atomicAdd(&s_hist[p][d], __popc(peers));
-        }
+    for (int d = 0; d < 4; d++) {
+        unsigned char *p = cnt + d * (RADIX * HIST_THREADS) + ((key >> (8 * d)) & 255u) * HIST_THREADS;
+        *p = (unsigned char)(*p + 1);
     }
+}
+
+__global__ void __launch_bounds__(HIST_THREADS, 1)
+radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned long long *__restrict__ hist) {
+    extern __shared__ __align__(16) unsigned char s_cnt[];
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *mine = s_cnt + lane * 4 + warp;
+    uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
+    for (int i = tid; i < HIST_SMEM / 16; i += HIST_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    unsigned total[HIST_ROWS_PER_THREAD];
+#pragma unroll
+    for (int r = 0; r < HIST_ROWS_PER_THREAD; r++) total[r] = 0;
     __syncthreads();
-    for (int j = threadIdx.x; j < 4 * RADIX; j += blockDim.x) {
-        unsigned c = (&s_hist[0][0])[j];
-        if (c) atomicAdd(hist + j, (unsigned long long)c);
+
+    // keys before the first 16-byte boundary (head) and after the last whole uint4 (tail): CTA 0, below.
+    // CTA c owns the contiguous chunk [c*per, (c+1)*per) of the aligned uint4 groups.
+    const long long head = min(n, (long long)(((16 - ((uintptr_t)keys & 15)) & 15) >> 2));
+    const long long groups = (n - head) >> 2;
+    const long long per = (groups + gridDim.x - 1) / gridDim.x;
+    long long g0 = (long long)blockIdx.x * per;
+    const long long g1 = min(groups, g0 + per);
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + head);
+    long long g = g0 + tid;
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (g < g1) cur = __ldg(k4 + g);
+    while (g0 < g1) {                                          // uniform: every thread runs the same trip count
+        const long long chunk_end = min(g1, g0 + (long long)HIST_ITERS_PER_FLUSH * HIST_THREADS);
+        for (; g0 < chunk_end; g0 += HIST_THREADS, g += HIST_THREADS) {
+            const bool have = g < g1;
+            const uint4 v = cur;
+            if (g + HIST_THREADS < g1) cur = __ldg(k4 + g + HIST_THREADS);   // next group in flight
+            if (have) {
+                hist_bump(mine, v.x); hist_bump(mine, v.y); hist_bump(mine, v.z); hist_bump(mine, v.w);
+            }
+        }
+        __syncthreads();
+        // flush: thread t sums rows t, t+128, ...; word index rotated by lane so the 32 lanes hit 32 banks
+#pragma unroll
+        for (int r = 0; r < HIST_ROWS_PER_THREAD; r++) {
+            uint32_t *row = reinterpret_cast<uint32_t *>(s_cnt + (size_t)(r * HIST_THREADS + tid) * HIST_THREADS);
+            unsigned acc = 0;
+#pragma unroll 8
+            for (int j = 0; j < 32; j++) {
+                const int wd = (j + lane) & 31;
+                acc = __dp4a(row[wd], 0x01010101u, acc);
+                row[wd] = 0;
+            }
+            total[r] += acc;
+        }
+        __syncthreads();
     }
+    if (blockIdx.x == 0 && tid == 0)                             // <= 3 head + <= 3 tail keys
+        for (long long i = 0; i < n; i++) {
+            if (i == head) i += groups << 2;
+            if (i >= n) break;
+            const uint32_t k = __ldg(keys + i);
+#pragma unroll
+            for (int d = 0; d < 4; d++) atomicAdd(hist + d * RADIX + ((k >> (8 * d)) & 255u), 1ull);
+        }
+#pragma unroll
+    for (int r = 0; r < HIST_ROWS_PER_THREAD; r++)
+        if (total[r]) atomicAdd(hist + r * HIST_THREADS + tid, (unsigned long long)total[r]);
 }
 
 // hist[4][256] -> exclusive prefix per pass (in place), one warp-scan per pass
@@ -373,8 +430,15 @@ extern "C" int mss_sort_pairs(uint32_t *keys, uint8_t *labs, int64_t n, void *wo
     MSS_CHECK_CUDA(cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, st));
     const size_t tiles = sort_tiles(n);
     MSS_REQUIRE(tiles < (1ull << 31), "mss_sort_pairs: n too large");
-    int hgrid = (int)std::min<long long>((n + 511) / 512, (long long)sm_count() * 4);
-    radix_histogram_kernel<<<hgrid, 512, 0, st>>>(keys, n, w.hist);
+    MSS_REQUIRE(((uintptr_t)keys & 3) == 0, "mss_sort_pairs: keys must be 4-byte aligned");
+    static std::atomic<bool> hist_attr{false};
+    if (!hist_attr.load()) {
+        MSS_CHECK_CUDA(cudaFuncSetAttribute(radix_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM));
+        hist_attr.store(true);
+    }
+    // one CTA per SM (128 KB of private counters each); small inputs use fewer CTAs (>= 8 K keys per CTA)
+    int hgrid = (int)std::max<long long>(1, std::min<long long>((n + 8191) / 8192, (long long)sm_count()));
+    radix_histogram_kernel<<<hgrid, HIST_THREADS, HIST_SMEM, st>>>(keys, n, w.hist);
     MSS_CHECK_LAUNCH();
     radix_scan_bins_kernel<<<1, RADIX, 0, st>>>(w.hist, 4);
     MSS_CHECK_LAUNCH();

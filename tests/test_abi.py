@@ -75,3 +75,39 @@ def test_missing_cuda_raises_instead_of_falling_back():
         metric.eval_ood_measure(np.zeros(4, np.float32), np.array([0, 1, 0, 1]))
     with pytest.raises(_lib.MssError):
         deeplab.energy_func(torch.zeros(1, 19, 4, 4))
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 128, 129, 1000, 4097, 100_003, 1_000_001, 12_345_678])
+def test_pairwise_tree_descent_matches_numpy_tree(lib_path, n):
+    """Host-only entry point: the table descent the device kernels use to find leaf i of numpy's
+    pairwise tree must give the leaves the oracle enumerates (oracle/metrics_oracle.py:pairwise_leaves,
+    itself pinned to np.sum by tests/test_oracle_metrics.py)."""
+    import ctypes as C
+    import random
+    from multishiftseg_b200 import _lib as L
+    from oracle import metrics_oracle as mo
+    lib = L.load()
+    want = mo.pairwise_leaves(n)
+    s, m, nl = C.c_int64(), C.c_int64(), C.c_int64()
+    rng = random.Random(n)
+    picks = range(len(want)) if len(want) <= 2000 else sorted(
+        {0, 1, len(want) - 2, len(want) - 1, *(rng.randrange(len(want)) for _ in range(2000))})
+    for i in picks:
+        assert lib.mss_pairwise_leaf_bounds(n, i, C.byref(s), C.byref(m), C.byref(nl)) == 0, L.last_error()
+        assert nl.value == len(want)
+        assert (s.value, m.value) == tuple(want[i])
+    assert lib.mss_pairwise_leaf_bounds(n, len(want), C.byref(s), C.byref(m), C.byref(nl)) < 0
+
+
+@pytest.mark.parametrize("n", [1, 5, 8, 127, 128, 129, 1000, 32768, 32769, 65_537, 1_000_003, 40_000_001])
+def test_pairwise_plan_and_combine_equal_numpy_sum(lib_path, n):
+    """plan (size table + frontier) -> leaf descent -> subtree combine -> top combine, run on the host through
+    the code shared with the device kernels, must reproduce np.sum bit for bit (ill-conditioned input)."""
+    import ctypes as C
+    import numpy as np
+    from multishiftseg_b200 import _lib as L
+    rng = np.random.default_rng(n)
+    a = (rng.standard_normal(n) * np.exp(rng.uniform(-20, 20, n))).astype(np.float64)
+    out = C.c_double()
+    assert L.load().mss_pairwise_sum_host(a.ctypes.data, n, C.byref(out)) == 0, L.last_error()
+    assert out.value == float(np.sum(a))
