@@ -28,6 +28,7 @@ SCORE_ENERGY, SCORE_MAXLOGIT, SCORE_MSP, SCORE_ENTROPY = 1, 2, 4, 8
 SCORE_BITS = {"energy": SCORE_ENERGY, "maxlogit": SCORE_MAXLOGIT, "msp": SCORE_MSP, "entropy": SCORE_ENTROPY}
 M2F_FORCE_GENERIC = 1
 M2F_FORCE_FFMA = 2
+M2F_FORCE_MMASYNC = 4
 EVAL_STATE_BYTES = 64
 
 

@@ -384,13 +384,14 @@ static EncodeTiledFn get_encode_fn() {
 }  // namespace mss
 
 #include "m2f_mma.cuh"
+#include "m2f_tc5.cuh"
 
 using namespace mss;
 
 extern "C" size_t mss_m2f_workspace_bytes(int64_t B, int Q, int C) {
     const int CPAD = (C + 3) / 4 * 4;
     return align_up((size_t)B * Q * CPAD * 4, 256) + align_up((size_t)B * Q * 4, 256) +
-           2 * align_up((size_t)B * MM_QPAD * MM_NPAD * 4, 256) + 512;
+           2 * align_up((size_t)B * T5_B_FLOATS * 4, 256) + 512;      // T5_B_FLOATS >= MM_QPAD * MM_NPAD
 }
 
 extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *mask_logits, int64_t B, int Q, int C,
@@ -412,8 +413,9 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
     Carver cv(workspace, workspace_bytes);
     float *probs = cv.take<float>((size_t)B * Q * CPAD);
     int *keep_slot = cv.take<int>((size_t)B * Q);
-    float *p_hi = cv.take<float>((size_t)B * MM_QPAD * MM_NPAD);
-    float *p_lo = cv.take<float>((size_t)B * MM_QPAD * MM_NPAD);
+    static_assert(T5_B_FLOATS >= MM_QPAD * MM_NPAD, "split class-probability tables share one workspace slot");
+    float *p_hi = cv.take<float>((size_t)B * T5_B_FLOATS);
+    float *p_lo = cv.take<float>((size_t)B * T5_B_FLOATS);
     if (!cv.ok()) {
         set_error("mss_m2f_semantic_inference: workspace too small (%zu < %zu)", workspace_bytes, mss_m2f_workspace_bytes(B, Q, C));
         return MSS_ERR_WORKSPACE;
@@ -433,12 +435,14 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
                     ((uintptr_t)mask_logits % 16 == 0) && B <= 65535;
     EncodeTiledFn enc = x4 ? get_encode_fn() : nullptr;
     const bool use_mma = x4 && enc && !(flags & MSS_M2F_FORCE_FFMA) && Q <= MM_QPAD - 4;
+    const bool use_tc5 = use_mma && !(flags & MSS_M2F_FORCE_MMASYNC);
     if (x4 && enc) {
         CUtensorMap tmap;
         cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(B * Q)};
         cuuint64_t gstr[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
         cuuint32_t box[3] = {BOX_W, BOX_H, QCHUNK};
         if (use_mma) { box[0] = MM_BOX_W; box[1] = MM_BOX_H; box[2] = MM_QPAD; }
+        if (use_tc5) { box[0] = T5_BOX_W; box[1] = T5_BOX_H; box[2] = T5_K; }
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)mask_logits, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -446,6 +450,24 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
         if (r != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
             return MSS_ERR_CUDA;
+        }
+        if (use_tc5) {
+            m2f_class_probs_umma_kernel<<<(unsigned)((B * T5_K + 127) / 128), 128, 0, st>>>(cls_logits, (int)B, Q, C + 1, p_hi, p_lo);
+            MSS_CHECK_LAUNCH();
+            static std::atomic<bool> tc5_attr_set{false};
+            if (!tc5_attr_set.load()) {
+                MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5_x4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM));
+                MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5_x4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM));
+                tc5_attr_set.store(true);
+            }
+            dim3 grid((Wc + T5_TILE_W - 1) / T5_TILE_W, (Hc + T5_BLOCK_H - 1) / T5_BLOCK_H, (unsigned)B);
+            MSS_REQUIRE(grid.y <= 65535, "mss_m2f_semantic_inference: grid too large");
+            if (has_extra)
+                m2f_tc5_x4_kernel<true><<<grid, T5_THREADS, T5_SMEM, st>>>(tmap, p_hi, p_lo, Q, h, w, out);
+            else
+                m2f_tc5_x4_kernel<false><<<grid, T5_THREADS, T5_SMEM, st>>>(tmap, p_hi, p_lo, Q, h, w, out);
+            MSS_CHECK_LAUNCH();
+            return MSS_OK;
         }
         if (use_mma) {
             m2f_class_probs_split_kernel<<<(unsigned)((B * MM_QPAD + 127) / 128), 128, 0, st>>>(cls_logits, (int)B, Q, C + 1,

@@ -95,8 +95,10 @@ runs_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restrict__ labs,
         if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
         return;
     }
+    // stage the tile's thresholds in shared memory (thread-order == output order), then write them out coalesced
+    __shared__ long long s_t[CT_TILE], s_f[CT_TILE];
     const Pair64 te = tile_excl[blockIdx.x];
-    unsigned long long kidx = te.a + ex.x;
+    unsigned slot = ex.x;
     unsigned long long cp = te.b + ex.y;
 #pragma unroll
     for (int j = 0; j < CT_IPT; j++) {
@@ -106,11 +108,16 @@ runs_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restrict__ labs,
             const bool end = (i == n - 1) || (k[j] != k[j + 1]);
             if (end) {
                 const long long t = pos_before + (long long)cp;
-                tps[kidx] = t;
-                fps[kidx] = idx_before + i + 1 - t;
-                kidx++;
+                s_t[slot] = t;
+                s_f[slot] = idx_before + i + 1 - t;
+                slot++;
             }
         }
+    }
+    __syncthreads();
+    for (unsigned q = threadIdx.x; q < tot.x; q += CT_THREADS) {
+        tps[te.a + q] = s_t[q];
+        fps[te.a + q] = s_f[q];
     }
 }
 
@@ -308,7 +315,7 @@ struct RocTerm {
 // n only, and the subtree sizes that occur in it are few (27 distinct sizes for n = 4 194 304 000), so
 // the host builds a table size -> #leaves and the device finds leaf i by descending from the root.
 constexpr int PW_MAX_SIZES = 256;
-constexpr int PW_MAX_FRONT = 8192;
+constexpr int PW_MAX_FRONT = 16384;
 
 __host__ __device__ __forceinline__ long long pw_split(long long m) {
     const long long n2 = m / 2;
@@ -344,15 +351,26 @@ struct PwTree {
     }
 };
 
+// one thread per leaf: start offsets of all leaves (leaf_start[n_leaves] = n)
+__global__ void __launch_bounds__(256)
+leaf_bounds_kernel(PwTree tree, long long *__restrict__ leaf_start) {
+    const long long leaf = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf > tree.n_leaves) return;
+    long long s = tree.n, m = 0;
+    if (leaf < tree.n_leaves) tree.leaf_bounds(leaf, s, m);
+    leaf_start[leaf] = s;
+}
+
 // 8 lanes per leaf = numpy's 8 interleaved accumulators
 template <typename Term>
 __global__ void __launch_bounds__(256)
-leaf_sum_kernel(Term term, PwTree tree, double *__restrict__ leaf_sum) {
+leaf_sum_kernel(Term term, const long long *__restrict__ leaf_start, long long n_leaves,
+                double *__restrict__ leaf_sum) {
     const long long leaf = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const unsigned sub = threadIdx.x & 7;
-    const bool live = leaf < tree.n_leaves;
-    long long s = 0, m = 0;
-    if (live) tree.leaf_bounds(leaf, s, m);
+    const bool live = leaf < n_leaves;
+    const long long s = live ? leaf_start[leaf] : 0;
+    const long long m = live ? leaf_start[leaf + 1] - s : 0;
     double res;
     if (m < 8) {
         // whole array shorter than 8 terms: sequential, starting from -0.0
@@ -465,7 +483,7 @@ static bool pw_plan(long long n, PwPlan &p) {
     for (auto &kv : memo) { p.size.push_back(kv.first); p.leaves.push_back(kv.second); }
     if (p.size.empty()) { p.size.push_back(129); p.leaves.push_back(2); }   // never looked up (n <= 128)
     // frontier granularity: nodes of <= F terms, F grown until there are at most ~PW_MAX_FRONT/2 nodes
-    p.F = 32768;
+    p.F = 2048;
     while (n / p.F > PW_MAX_FRONT / 4) p.F *= 2;
     long long leaf = 0;
     pw_frontier(n, p.F, leaf, memo, p.front);
@@ -483,7 +501,7 @@ static double pw_combine_top(const double *node_sum, size_t &next, long long m, 
 }
 
 struct PwDevice {
-    long long *size, *leaves;
+    long long *size, *leaves, *leaf_start;
     PwFrontNode *front;
     double *node_sum;
 };
@@ -544,12 +562,14 @@ extern "C" size_t mss_tail_workspace_bytes(int64_t T) {
     return 2 * align_up((size_t)T * 8, 256)                      /* tps_k, fps_k */
            + ct_tiles(T) * (sizeof(uint2) + sizeof(Pair64) + sizeof(Best)) + 1024   /* compaction tiles, FPR95 candidates */
            + 2 * align_up(leaves * 8, 256)                       /* leaf sums (AP, ROC) */
+           + 2 * align_up((leaves + 1) * 8, 256)                 /* leaf starts (AP, ROC) */
            + 2 * pw_device_bytes()                               /* tree tables + frontier (AP, ROC) */
            + 1024 * sizeof(Best) + 8192;
 }
 
-static PwDevice pw_carve(Carver &c) {
+static PwDevice pw_carve(Carver &c, size_t max_leaves) {
     PwDevice d;
+    d.leaf_start = c.take<long long>(max_leaves + 1);
     d.size = c.take<long long>(PW_MAX_SIZES);
     d.leaves = c.take<long long>(PW_MAX_SIZES);
     d.front = c.take<PwFrontNode>(PW_MAX_FRONT);
@@ -564,7 +584,9 @@ static int pw_launch(const PwPlan &p, const PwDevice &d, Term term, double *leaf
     MSS_CHECK_CUDA(cudaMemcpyAsync(d.leaves, p.leaves.data(), p.leaves.size() * 8, cudaMemcpyHostToDevice, st));
     MSS_CHECK_CUDA(cudaMemcpyAsync(d.front, p.front.data(), p.front.size() * sizeof(PwFrontNode), cudaMemcpyHostToDevice, st));
     PwTree tree{d.size, d.leaves, (int)p.size.size(), p.n, p.n_leaves};
-    leaf_sum_kernel<Term><<<(unsigned)((p.n_leaves * 8 + 255) / 256), 256, 0, st>>>(term, tree, leaf_sum);
+    leaf_bounds_kernel<<<(unsigned)((p.n_leaves + 1 + 255) / 256), 256, 0, st>>>(tree, d.leaf_start);
+    MSS_CHECK_LAUNCH();
+    leaf_sum_kernel<Term><<<(unsigned)((p.n_leaves * 8 + 255) / 256), 256, 0, st>>>(term, d.leaf_start, p.n_leaves, leaf_sum);
     MSS_CHECK_LAUNCH();
     const int nf = (int)p.front.size();
     subtree_combine_kernel<<<(nf + 127) / 128, 128, 0, st>>>(d.front, nf, leaf_sum, d.node_sum);
@@ -588,7 +610,7 @@ extern "C" int mss_metrics_tail(const int64_t *tps_, const int64_t *fps_, int64_
     Best *tile_best = c.take<Best>(tiles);
     double *sum_ap = c.take<double>(max_leaves);
     double *sum_roc = c.take<double>(max_leaves);
-    PwDevice d_ap = pw_carve(c), d_roc = pw_carve(c);
+    PwDevice d_ap = pw_carve(c, max_leaves), d_roc = pw_carve(c, max_leaves);
     Best *partial = c.take<Best>(1024);
     unsigned long long *totals = c.take<unsigned long long>(2);
     double *fpr_out = c.take<double>(1);

@@ -59,90 +59,72 @@ __device__ __forceinline__ unsigned match_bits(unsigned d, bool valid) {
 }
 
 // ---- upfront histogram of the four digits ------------------------------------------------------------
-// Shared-memory atomics cost ~1-2 cycles per LANE on sm_100 (ncu, round 1: the warp-aggregated atomic
-// version of this kernel took 436 us for 32 M keys, 20x its HBM time), and the digits of real score
-// distributions are extremely skewed (sign/exponent bits; zeroed mantissa bits of fp16-born scores), so
-// contention-sensitive schemes are out.  Instead every thread owns a PRIVATE set of 8-bit counters,
-// 4 digits x 256 bins, updated with plain byte load / add / byte store: no atomics, no dependence on the
-// key distribution.  Counter (digit d, bin b) of thread (warp w, lane l) lives at byte
-//     d*32768 + b*128 + l*4 + w
-// so a warp's 32 accesses always fall into 32 different banks whatever the bins are.  A thread handles at
-// most 252 keys between two flushes (8-bit counters cannot overflow); a flush sums each 128-byte row
-// (= the 128 threads' counters of one bin) with dp4a into per-thread 32-bit running totals.
+// Shared-memory atomics cost ~1-2 cycles per LANE on sm_100 (ncu, round 1: a warp-aggregated atomic version
+// of this kernel took 436 us for 32 M keys, 20x its HBM time; byte-wide private counters 228 us), and the
+// digits of real score distributions are extremely skewed (sign/exponent bits; zeroed mantissa bits of
+// fp16-born scores), so contention-sensitive schemes are out.  Here every LANE owns private 32-bit counters:
+// warp d of the CTA counts digit d of ALL the CTA's keys (the four warps read the same keys; the re-reads
+// hit L1/L2), counter (bin b, lane l) of warp d lives at word d*8192 + b*32 + l, i.e. always in bank l:
+// plain load / add / store, no atomics, no bank conflicts, no dependence on the key distribution.
+// Four keys are in flight per lane; equal bins among them are merged in registers before the stores.
 constexpr int HIST_THREADS = 128;
-constexpr int HIST_ROWS = 4 * RADIX;                       // (digit, bin) rows of 128 bytes
-constexpr int HIST_SMEM = HIST_ROWS * HIST_THREADS;        // 131072 bytes
-constexpr int HIST_ITERS_PER_FLUSH = 63;                   // x 4 keys per thread per iteration = 252
-constexpr int HIST_ROWS_PER_THREAD = HIST_ROWS / HIST_THREADS;   // 8
-
-__device__ __forceinline__ void hist_bump(unsigned char *cnt, uint32_t key) {
-#pragma unroll
-    for (int d = 0; d < 4; d++) {
-        unsigned char *p = cnt + d * (RADIX * HIST_THREADS) + ((key >> (8 * d)) & 255u) * HIST_THREADS;
-        *p = (unsigned char)(*p + 1);
-    }
-}
+constexpr int HIST_SMEM = 4 * RADIX * 32 * 4;              // 131072 bytes
+constexpr int HIST_KPT = 4;                                 // keys per lane per iteration (one uint4)
 
 __global__ void __launch_bounds__(HIST_THREADS, 1)
 radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned long long *__restrict__ hist) {
-    extern __shared__ __align__(16) unsigned char s_cnt[];
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned char *mine = s_cnt + lane * 4 + warp;
-    uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
-    for (int i = tid; i < HIST_SMEM / 16; i += HIST_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-    unsigned total[HIST_ROWS_PER_THREAD];
-#pragma unroll
-    for (int r = 0; r < HIST_ROWS_PER_THREAD; r++) total[r] = 0;
+    extern __shared__ __align__(16) unsigned s_cnt[];
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;     // warp == digit
+    for (int i = tid; i < HIST_SMEM / 16; i += HIST_THREADS) reinterpret_cast<uint4 *>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
+    const uint32_t mine = (uint32_t)__cvta_generic_to_shared(s_cnt) + warp * (RADIX * 32 * 4) + lane * 4;
+    const int shift = 8 * warp;
 
     // keys before the first 16-byte boundary (head) and after the last whole uint4 (tail): CTA 0, below.
-    // CTA c owns the contiguous chunk [c*per, (c+1)*per) of the aligned uint4 groups.
+    // CTA c owns the contiguous chunk [c*per, (c+1)*per) of the aligned uint4 groups; each of its warps walks it.
     const long long head = min(n, (long long)(((16 - ((uintptr_t)keys & 15)) & 15) >> 2));
     const long long groups = (n - head) >> 2;
     const long long per = (groups + gridDim.x - 1) / gridDim.x;
-    long long g0 = (long long)blockIdx.x * per;
-    const long long g1 = min(groups, g0 + per);
+    const long long g0 = (long long)blockIdx.x * per, g1 = min(groups, g0 + per);
     const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + head);
-    long long g = g0 + tid;
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (g < g1) cur = __ldg(k4 + g);
-    while (g0 < g1) {                                          // uniform: every thread runs the same trip count
-        const long long chunk_end = min(g1, g0 + (long long)HIST_ITERS_PER_FLUSH * HIST_THREADS);
-        for (; g0 < chunk_end; g0 += HIST_THREADS, g += HIST_THREADS) {
-            const bool have = g < g1;
-            const uint4 v = cur;
-            if (g + HIST_THREADS < g1) cur = __ldg(k4 + g + HIST_THREADS);   // next group in flight
-            if (have) {
-                hist_bump(mine, v.x); hist_bump(mine, v.y); hist_bump(mine, v.z); hist_bump(mine, v.w);
-            }
-        }
-        __syncthreads();
-        // flush: thread t sums rows t, t+128, ...; word index rotated by lane so the 32 lanes hit 32 banks
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (g0 + lane < g1) nxt = __ldg(k4 + g0 + lane);
+    for (long long g = g0 + lane; g < g1; g += 32) {
+        const uint4 v = nxt;
+        if (g + 32 < g1) nxt = __ldg(k4 + g + 32);         // next group in flight
+        const uint32_t k[HIST_KPT] = {v.x, v.y, v.z, v.w};
+        uint32_t a[HIST_KPT], c[HIST_KPT];
 #pragma unroll
-        for (int r = 0; r < HIST_ROWS_PER_THREAD; r++) {
-            uint32_t *row = reinterpret_cast<uint32_t *>(s_cnt + (size_t)(r * HIST_THREADS + tid) * HIST_THREADS);
-            unsigned acc = 0;
+        for (int j = 0; j < HIST_KPT; j++) a[j] = mine + (((k[j] >> shift) & 255u) << 7);
+        // multiplicity of each key's bin among the lane's four keys (equal bins all store the same total)
+        const unsigned e01 = a[0] == a[1], e02 = a[0] == a[2], e03 = a[0] == a[3];
+        const unsigned e12 = a[1] == a[2], e13 = a[1] == a[3], e23 = a[2] == a[3];
+        const unsigned add[HIST_KPT] = {1 + e01 + e02 + e03, 1 + e01 + e12 + e13, 1 + e02 + e12 + e23, 1 + e03 + e13 + e23};
+#pragma unroll
+        for (int j = 0; j < HIST_KPT; j++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c[j]) : "r"(a[j]));
+#pragma unroll
+        for (int j = 0; j < HIST_KPT; j++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a[j]), "r"(c[j] + add[j]) : "memory");
+    }
+    __syncwarp();
+    // per-bin totals of this warp's digit: lane l sums bins l, l+32, ...; word index rotated so that the 32
+    // lanes hit 32 different banks
+    const unsigned *wbase = s_cnt + warp * (RADIX * 32);
+#pragma unroll 1
+    for (int r = 0; r < RADIX / 32; r++) {
+        const int bin = r * 32 + lane;
+        unsigned acc = 0;
 #pragma unroll 8
-            for (int j = 0; j < 32; j++) {
-                const int wd = (j + lane) & 31;
-                acc = __dp4a(row[wd], 0x01010101u, acc);
-                row[wd] = 0;
-            }
-            total[r] += acc;
-        }
-        __syncthreads();
+        for (int j = 0; j < 32; j++) acc += wbase[bin * 32 + ((j + lane) & 31)];
+        if (acc) atomicAdd(hist + warp * RADIX + bin, (unsigned long long)acc);
     }
     if (blockIdx.x == 0 && tid == 0)                             // <= 3 head + <= 3 tail keys
         for (long long i = 0; i < n; i++) {
             if (i == head) i += groups << 2;
             if (i >= n) break;
-            const uint32_t k = __ldg(keys + i);
+            const uint32_t kk = __ldg(keys + i);
 #pragma unroll
-            for (int d = 0; d < 4; d++) atomicAdd(hist + d * RADIX + ((k >> (8 * d)) & 255u), 1ull);
+            for (int d = 0; d < 4; d++) atomicAdd(hist + d * RADIX + ((kk >> (8 * d)) & 255u), 1ull);
         }
-#pragma unroll
-    for (int r = 0; r < HIST_ROWS_PER_THREAD; r++)
-        if (total[r]) atomicAdd(hist + r * HIST_THREADS + tid, (unsigned long long)total[r]);
 }
 
 // hist[4][256] -> exclusive prefix per pass (in place), one warp-scan per pass
