@@ -201,6 +201,26 @@ MSS_API int mss_pairwise_leaf_bounds(int64_t n, int64_t leaf, int64_t *start_hos
 MSS_API int mss_pairwise_sum_host(const double *terms_host, int64_t n, double *out_host);
 
 /* ---------------------------------------------------------------------------------------------
+ *  mIoU half of lib/utils/metric.py: the confusion histogram of hist_info (:10-18),
+ *   k = (gt >= 0) & (gt < n_cl); labeled = sum(k); correct = sum(pred[k] == gt[k]);
+ *   hist = bincount(n_cl * gt[k] + pred[k], minlength = n_cl^2).reshape(n_cl, n_cl)
+ * ACCUMULATED (+=) into caller-owned, caller-zeroed device int64 buffers, which is compute_metric's
+ * `hist += d['hist']; correct += ...; labeled += ...` loop (:21-33) kept on the device:
+ *   hist [n_cl * n_cl] int64 (row = gt, column = pred), labeled_correct [3] int64 = {labeled, correct,
+ *   out-of-range count}.  n_cl <= 32.  A labeled pixel whose n_cl*gt + pred falls outside [0, n_cl^2)
+ * makes numpy raise; here it is counted in labeled_correct[2] and the call returns MSS_ERR_INVALID_ARG.
+ * Both calls synchronise `stream` (to read that flag).
+ * ------------------------------------------------------------------------------------------- */
+/* pred, gt: class-index maps [n] of MSS_LABEL_* element types */
+MSS_API int mss_confusion_hist(const void *pred, int pred_dtype, const void *gt, int gt_dtype, int64_t n,
+                       int n_cl, int64_t *hist, int64_t *labeled_correct, void *stream);
+/* fused: pred = argmax_c logits[b, c, p] (torch.argmax: first maximal index) over NCHW fp32 logits
+ * [B, C, HW], never written to memory */
+MSS_API int mss_confusion_from_logits(const float *logits, int64_t B, int C, int64_t HW, const void *gt,
+                              int gt_dtype, int n_cl, int64_t *hist, int64_t *labeled_correct,
+                              void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points: what a reference-side caller holding numpy / CPU tensors would call.
  * Inputs and outputs are HOST pointers (pinned memory recommended); the library stages them
  * through caller-provided device scratch in chunks, overlapping H2D, kernel and D2H on internal

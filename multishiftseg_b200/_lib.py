@@ -71,6 +71,8 @@ SIGNATURES = {
     "mss_metrics_tail": (_i, [_p, _p, _i64, _d, _p, _sz, _p, _p, _p]),
     "mss_pairwise_leaf_bounds": (_i, [_i64, _i64, _p, _p, _p]),
     "mss_pairwise_sum_host": (_i, [_p, _i64, _p]),
+    "mss_confusion_hist": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p, _p]),
+    "mss_confusion_from_logits": (_i, [_p, _i64, _i, _i64, _p, _i, _i, _p, _p, _p]),
     "mss_deeplab_score_host_scratch_bytes": (_sz, [_i64, _i, _i64, _u]),
     "mss_deeplab_score_host": (_i, [_p, _i64, _i, _i64, _u, _p, _p, _p, _p, _p, _sz, _p]),
 }

@@ -12,6 +12,8 @@
 //
 // The same scatter kernel, with the digit replaced by "which key range does this key fall in"
 // (SplitterDigit), is the local half of the multi-GPU key-range exchange (mss_partition_pairs).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mss {
@@ -59,67 +61,139 @@ __device__ __forceinline__ unsigned match_bits(unsigned d, bool valid) {
 }
 
 // ---- upfront histogram of the four digits ------------------------------------------------------------
-// Shared-memory atomics cost ~1-2 cycles per LANE on sm_100 (ncu, round 1: a warp-aggregated atomic version
-// of this kernel took 436 us for 32 M keys, 20x its HBM time; byte-wide private counters 228 us), and the
-// digits of real score distributions are extremely skewed (sign/exponent bits; zeroed mantissa bits of
-// fp16-born scores), so contention-sensitive schemes are out.  Here every LANE owns private 32-bit counters:
-// warp d of the CTA counts digit d of ALL the CTA's keys (the four warps read the same keys; the re-reads
-// hit L1/L2), counter (bin b, lane l) of warp d lives at word d*8192 + b*32 + l, i.e. always in bank l:
-// plain load / add / store, no atomics, no bank conflicts, no dependence on the key distribution.
-// Four keys are in flight per lane; equal bins among them are merged in registers before the stores.
-constexpr int HIST_THREADS = 128;
-constexpr int HIST_SMEM = 4 * RADIX * 32 * 4;              // 131072 bytes
-constexpr int HIST_KPT = 4;                                 // keys per lane per iteration (one uint4)
+// Shared-memory atomics cost ~1-2 cycles per LANE on sm_100 and the digits of real score distributions are
+// extremely skewed (sign/exponent bits; zeroed mantissa bits of fp16-born scores), so contention-sensitive
+// schemes are out.  Every LANE owns private counters instead -- plain load / add / store, no atomics, no
+// dependence on the key distribution.  ncu (round 1, 32 M keys) on the first form of this idea, 4 warps per
+// SM with 32-bit counters and register-prefetched global loads: 814 us, issue 6.5 %, 4 of 64 warp slots --
+// pure latency.  This form:
+//   * 16-bit counters (16 KB per warp) -> 12 warps per SM: warp = (group g of 3, digit d of 4); the four
+//     digit-warps of a group count the same keys, the three groups split every chunk;
+//     counter (bin b, lane l) of a warp is the halfword at b*64 + 2*l;
+//   * keys arrive through a 4-stage ring of 6 KB bulk copies (cp.async.bulk + mbarrier, one elected lane),
+//     which keeps ~18 KB per SM in flight instead of 1.5 KB;
+//   * a lane adds at most 16 to one counter per chunk, so counters are folded into 32-bit per-CTA totals every
+//     HIST_EPOCH (<= 4095) chunks -- warp-local, no CTA barrier.
+// Two keys are in flight per lane; when they hit the same counter both store the merged total.
+constexpr int HIST_WARPS = 12;
+constexpr int HIST_THREADS = HIST_WARPS * 32;                  // 384
+constexpr int HIST_GROUPS = HIST_WARPS / 4;                    // 3
+constexpr int HIST_CHUNK_KEYS = HIST_GROUPS * 32 * 4 * 4;      // 1536 keys = 6 KB: 4 uint4 per lane per group
+constexpr int HIST_CHUNK_BYTES = HIST_CHUNK_KEYS * 4;
+constexpr int HIST_STAGES = 4;
+constexpr int HIST_WARP_BYTES = RADIX * 32 * 2;                // 16 KB of u16 counters
+constexpr int HIST_EPOCH = 4000;
+constexpr int HIST_SMEM = HIST_WARPS * HIST_WARP_BYTES + HIST_STAGES * HIST_CHUNK_BYTES + 4 * RADIX * 4 +
+                          2 * HIST_STAGES * 8 + 128;
+
+__device__ __forceinline__ unsigned lds_u16(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, unsigned v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
 
 __global__ void __launch_bounds__(HIST_THREADS, 1)
-radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned long long *__restrict__ hist) {
-    extern __shared__ __align__(16) unsigned s_cnt[];
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;     // warp == digit
-    for (int i = tid; i < HIST_SMEM / 16; i += HIST_THREADS) reinterpret_cast<uint4 *>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
+radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned long long *__restrict__ hist,
+                       int epoch_chunks) {
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    unsigned char *s_cnt = s_raw;                                                  // [12][256][32] u16
+    uint4 *s_ring = reinterpret_cast<uint4 *>(s_raw + HIST_WARPS * HIST_WARP_BYTES);   // [4][384] uint4
+    unsigned *s_tot = reinterpret_cast<unsigned *>(s_ring + HIST_STAGES * (HIST_CHUNK_KEYS / 4));   // [4][256]
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s_tot + 4 * RADIX), *s_empty = s_full + HIST_STAGES;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned digit = warp & 3, group = warp >> 2;
+
+    for (int i = tid; i < HIST_WARPS * HIST_WARP_BYTES / 16; i += HIST_THREADS)
+        reinterpret_cast<uint4 *>(s_cnt)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 4 * RADIX; i += HIST_THREADS) s_tot[i] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < HIST_STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], HIST_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    const uint32_t mine = (uint32_t)__cvta_generic_to_shared(s_cnt) + warp * (RADIX * 32 * 4) + lane * 4;
-    const int shift = 8 * warp;
 
     // keys before the first 16-byte boundary (head) and after the last whole uint4 (tail): CTA 0, below.
-    // CTA c owns the contiguous chunk [c*per, (c+1)*per) of the aligned uint4 groups; each of its warps walks it.
     const long long head = min(n, (long long)(((16 - ((uintptr_t)keys & 15)) & 15) >> 2));
-    const long long groups = (n - head) >> 2;
-    const long long per = (groups + gridDim.x - 1) / gridDim.x;
-    const long long g0 = (long long)blockIdx.x * per, g1 = min(groups, g0 + per);
+    const long long groups4 = (n - head) >> 2;                                     // whole uint4 groups
     const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + head);
-    uint4 nxt = make_uint4(0, 0, 0, 0);
-    if (g0 + lane < g1) nxt = __ldg(k4 + g0 + lane);
-    for (long long g = g0 + lane; g < g1; g += 32) {
-        const uint4 v = nxt;
-        if (g + 32 < g1) nxt = __ldg(k4 + g + 32);         // next group in flight
-        const uint32_t k[HIST_KPT] = {v.x, v.y, v.z, v.w};
-        uint32_t a[HIST_KPT], c[HIST_KPT];
-#pragma unroll
-        for (int j = 0; j < HIST_KPT; j++) a[j] = mine + (((k[j] >> shift) & 255u) << 7);
-        // multiplicity of each key's bin among the lane's four keys (equal bins all store the same total)
-        const unsigned e01 = a[0] == a[1], e02 = a[0] == a[2], e03 = a[0] == a[3];
-        const unsigned e12 = a[1] == a[2], e13 = a[1] == a[3], e23 = a[2] == a[3];
-        const unsigned add[HIST_KPT] = {1 + e01 + e02 + e03, 1 + e01 + e12 + e13, 1 + e02 + e12 + e23, 1 + e03 + e13 + e23};
-#pragma unroll
-        for (int j = 0; j < HIST_KPT; j++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c[j]) : "r"(a[j]));
-#pragma unroll
-        for (int j = 0; j < HIST_KPT; j++) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a[j]), "r"(c[j] + add[j]) : "memory");
-    }
-    __syncwarp();
-    // per-bin totals of this warp's digit: lane l sums bins l, l+32, ...; word index rotated so that the 32
-    // lanes hit 32 different banks
-    const unsigned *wbase = s_cnt + warp * (RADIX * 32);
+    const long long chunks = (groups4 + HIST_CHUNK_KEYS / 4 - 1) / (HIST_CHUNK_KEYS / 4);
+    // CTA c owns chunks c, c + grid, ...
+    const long long my_chunks = (chunks > (long long)blockIdx.x) ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](long long j) {                                                // elected lane only
+        const long long c = (long long)blockIdx.x + j * gridDim.x;
+        const long long g0 = c * (HIST_CHUNK_KEYS / 4);
+        const unsigned bytes = (unsigned)(min((long long)(HIST_CHUNK_KEYS / 4), groups4 - g0) * 16);
+        const int s = (int)(j % HIST_STAGES);
+        mbar_expect_tx(&s_full[s], bytes);
+        bulk_load_1d(s_ring + s * (HIST_CHUNK_KEYS / 4), k4 + g0, bytes, &s_full[s]);
+    };
+    if (tid == 0)
+        for (long long j = 0; j < HIST_STAGES && j < my_chunks; j++) issue(j);
+
+    const uint32_t mine = smem_u32(s_cnt) + warp * HIST_WARP_BYTES + lane * 2;
+    const int shift = 8 * (int)digit;
+    // fold this warp's 16-bit counters into the CTA totals of its digit and zero them (warp-local)
+    auto fold = [&]() {
+        __syncwarp();
+        uint32_t *w32 = reinterpret_cast<uint32_t *>(s_cnt + warp * HIST_WARP_BYTES);
 #pragma unroll 1
-    for (int r = 0; r < RADIX / 32; r++) {
-        const int bin = r * 32 + lane;
-        unsigned acc = 0;
-#pragma unroll 8
-        for (int j = 0; j < 32; j++) acc += wbase[bin * 32 + ((j + lane) & 31)];
-        if (acc) atomicAdd(hist + warp * RADIX + bin, (unsigned long long)acc);
+        for (int r = 0; r < RADIX / 32; r++) {
+            const int bin = r * 32 + lane;
+            unsigned acc = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {                                         // rotated: 32 lanes, 32 banks
+                const int wi = bin * 16 + ((j + (lane >> 1)) & 15);
+                const uint32_t v = w32[wi];
+                acc += (v & 0xffffu) + (v >> 16);
+                w32[wi] = 0;
+            }
+            if (acc) atomicAdd(&s_tot[digit * RADIX + bin], acc);
+        }
+        __syncwarp();
+    };
+
+    int in_epoch = 0;
+    for (long long j = 0; j < my_chunks; j++) {
+        const int s = (int)(j % HIST_STAGES);
+        const unsigned parity = (unsigned)((j / HIST_STAGES) & 1);
+        mbar_wait(&s_full[s], parity);
+        const long long c = (long long)blockIdx.x + j * gridDim.x;
+        const int valid4 = (int)min((long long)(HIST_CHUNK_KEYS / 4), groups4 - c * (HIST_CHUNK_KEYS / 4));
+        const uint4 *src = s_ring + s * (HIST_CHUNK_KEYS / 4) + group * 128 + lane;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            if ((int)(group * 128 + it * 32 + lane) < valid4) {
+                const uint4 v = src[it * 32];
+                const uint32_t k[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int h = 0; h < 4; h += 2) {
+                    const uint32_t a0 = mine + (((k[h] >> shift) & 255u) << 6);
+                    const uint32_t a1 = mine + (((k[h + 1] >> shift) & 255u) << 6);
+                    const unsigned add = 1u + (a0 == a1);
+                    const unsigned c0 = lds_u16(a0), c1 = lds_u16(a1);
+                    sts_u16(a0, c0 + add);
+                    sts_u16(a1, c1 + add);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_one(&s_empty[s]);
+        if (tid == 0 && j + HIST_STAGES < my_chunks) {                             // refill the stage just drained
+            mbar_wait(&s_empty[s], parity);
+            issue(j + HIST_STAGES);
+        }
+        if (++in_epoch == epoch_chunks) { fold(); in_epoch = 0; }
     }
+    fold();
+    __syncthreads();
+    for (int i = tid; i < 4 * RADIX; i += HIST_THREADS)
+        if (s_tot[i]) atomicAdd(hist + i, (unsigned long long)s_tot[i]);
     if (blockIdx.x == 0 && tid == 0)                             // <= 3 head + <= 3 tail keys
         for (long long i = 0; i < n; i++) {
-            if (i == head) i += groups << 2;
+            if (i == head) i += groups4 << 2;
             if (i >= n) break;
             const uint32_t kk = __ldg(keys + i);
 #pragma unroll
@@ -364,6 +438,16 @@ keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift,
     }
 }
 
+// test hook: MSS_HIST_EPOCH=<chunks> shortens the counter-fold period so small inputs exercise it
+static int hist_epoch_chunks() {
+    static const int v = [] {
+        const char *e = getenv("MSS_HIST_EPOCH");
+        const int x = e ? atoi(e) : HIST_EPOCH;
+        return (x >= 1 && x <= HIST_EPOCH) ? x : HIST_EPOCH;
+    }();
+    return v;
+}
+
 static size_t sort_tiles(int64_t n) { return (size_t)((n + SORT_TILE - 1) / SORT_TILE); }
 
 struct SortWs {
@@ -418,9 +502,10 @@ extern "C" int mss_sort_pairs(uint32_t *keys, uint8_t *labs, int64_t n, void *wo
         MSS_CHECK_CUDA(cudaFuncSetAttribute(radix_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM));
         hist_attr.store(true);
     }
-    // one CTA per SM (128 KB of private counters each); small inputs use fewer CTAs (>= 8 K keys per CTA)
-    int hgrid = (int)std::max<long long>(1, std::min<long long>((n + 8191) / 8192, (long long)sm_count()));
-    radix_histogram_kernel<<<hgrid, HIST_THREADS, HIST_SMEM, st>>>(keys, n, w.hist);
+    // one CTA per SM (192 KB of private counters each); small inputs use fewer CTAs (>= 4 chunks per CTA)
+    int hgrid = (int)std::max<long long>(1, std::min<long long>((n + 4 * HIST_CHUNK_KEYS - 1) / (4 * HIST_CHUNK_KEYS),
+                                                                (long long)sm_count()));
+    radix_histogram_kernel<<<hgrid, HIST_THREADS, HIST_SMEM, st>>>(keys, n, w.hist, hist_epoch_chunks());
     MSS_CHECK_LAUNCH();
     radix_scan_bins_kernel<<<1, RADIX, 0, st>>>(w.hist, 4);
     MSS_CHECK_LAUNCH();

@@ -127,6 +127,35 @@ def test_sort_pairs_exact(M):
         assert np.array_equal(vt.cpu().numpy(), v[order])       # stable: payload follows input order inside ties
 
 
+def test_sort_pairs_histogram_counter_fold():
+    """The upfront digit histogram keeps 16-bit lane-private counters and folds them every HIST_EPOCH chunks;
+    MSS_HIST_EPOCH=2 (read once per process) makes a 5 M-key input cross many folds.  Unaligned key pointer too."""
+    import subprocess
+    import sys
+    code = r"""
+import numpy as np, torch, sys
+sys.path.insert(0, ".")
+from multishiftseg_b200 import metric as M
+rng = np.random.default_rng(3)
+n = 5_000_003
+k = rng.integers(0, 2 ** 32, size=n + 1, dtype=np.uint64).astype(np.uint32)
+k[: n // 2] &= np.uint32(0x0000FFFF)
+k[n // 2: n // 2 + n // 4] |= np.uint32(0xFFFF0000)
+v = rng.integers(0, 2, size=n + 1, dtype=np.uint8)
+kt = torch.from_numpy(k.view(np.int32)).cuda()[1:]          # 4-byte aligned, not 16
+vt = torch.from_numpy(v).cuda()[1:].clone()
+M.sort_pairs(kt, vt, n)
+order = np.argsort(k[1:], kind="stable")
+assert np.array_equal(kt.cpu().numpy().view(np.uint32), k[1:][order])
+assert np.array_equal(vt.cpu().numpy(), v[1:][order])
+print("fold ok")
+"""
+    env = dict(os.environ, MSS_HIST_EPOCH="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "fold ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_counts_and_tail_stage_level(M):
     s, l = gi.metric_case(11, 300_000, "f16", label_dtype="uint8")
     tps_ref, fps_ref = mo.ood_counts(s, l)
