@@ -132,6 +132,7 @@ MSS_API int mss_deeplab_anomaly_score(const float *ood_logits, int64_t B, int C,
 #define MSS_M2F_FORCE_GENERIC 1u   /* any-resize kernel (no TMA) */
 #define MSS_M2F_FORCE_FFMA 2u      /* TMA-staged x4 kernel with the FP32-FMA contraction instead of the 3xTF32 tensor-core one */
 #define MSS_M2F_FORCE_MMASYNC 4u   /* 3xTF32 contraction through mma.sync (legacy tensor path) instead of tcgen05 + TMEM */
+#define MSS_M2F_FORCE_TC5_PIXEL 8u /* tcgen05 kernel with one pixel per thread (first form) instead of the shared-tap 4x1 blocks */
 MSS_API size_t mss_m2f_workspace_bytes(int64_t B, int Q, int C);
 MSS_API int mss_m2f_semantic_inference(const float *cls_logits, const float *mask_logits,
                                int64_t B, int Q, int C, int h, int w, int Hp, int Wp, int Hc, int Wc,

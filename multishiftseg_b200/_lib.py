@@ -29,6 +29,7 @@ SCORE_BITS = {"energy": SCORE_ENERGY, "maxlogit": SCORE_MAXLOGIT, "msp": SCORE_M
 M2F_FORCE_GENERIC = 1
 M2F_FORCE_FFMA = 2
 M2F_FORCE_MMASYNC = 4
+M2F_FORCE_TC5_PIXEL = 8
 EVAL_STATE_BYTES = 64
 
 

@@ -369,6 +369,7 @@ static EncodeTiledFn get_encode_fn() {
 
 #include "m2f_mma.cuh"
 #include "m2f_tc5.cuh"
+#include "m2f_tc5q.cuh"
 
 using namespace mss;
 
@@ -420,6 +421,7 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
     EncodeTiledFn enc = x4 ? get_encode_fn() : nullptr;
     const bool use_mma = x4 && enc && !(flags & MSS_M2F_FORCE_FFMA) && Q <= MM_QPAD - 4;
     const bool use_tc5 = use_mma && !(flags & MSS_M2F_FORCE_MMASYNC);
+    const bool use_tc5q = use_tc5 && !(flags & MSS_M2F_FORCE_TC5_PIXEL);
     if (x4 && enc) {
         CUtensorMap tmap;
         cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(B * Q)};
@@ -427,6 +429,7 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
         cuuint32_t box[3] = {BOX_W, BOX_H, QCHUNK};
         if (use_mma) { box[0] = MM_BOX_W; box[1] = MM_BOX_H; box[2] = MM_QPAD; }
         if (use_tc5) { box[0] = T5_BOX_W; box[1] = T5_BOX_H; box[2] = T5_K; }
+        if (use_tc5q) { box[0] = TQ_BOX_W; box[1] = TQ_BOX_H; box[2] = T5_K; }
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)mask_logits, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -438,6 +441,23 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
         if (use_tc5) {
             m2f_class_probs_umma_kernel<<<(unsigned)((B * T5_K + 127) / 128), 128, 0, st>>>(cls_logits, (int)B, Q, C + 1, p_hi, p_lo);
             MSS_CHECK_LAUNCH();
+            if (use_tc5q) {
+                static std::atomic<bool> tq_attr_set{false};
+                if (!tq_attr_set.load()) {
+                    MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TQ_SMEM));
+                    MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TQ_SMEM));
+                    tq_attr_set.store(true);
+                }
+                // blocks of 4 pixels start at x = 2 (mod 4): CTA bx covers x in [64 bx - 2, 64 bx + 62)
+                dim3 grid((Wc + 2 + TQ_W - 1) / TQ_W, (Hc + TQ_H - 1) / TQ_H, (unsigned)B);
+                MSS_REQUIRE(grid.y <= 65535, "mss_m2f_semantic_inference: grid too large");
+                if (has_extra)
+                    m2f_tc5q_kernel<true><<<grid, TQ_THREADS, TQ_SMEM, st>>>(tmap, p_hi, p_lo, Q, h, w, out);
+                else
+                    m2f_tc5q_kernel<false><<<grid, TQ_THREADS, TQ_SMEM, st>>>(tmap, p_hi, p_lo, Q, h, w, out);
+                MSS_CHECK_LAUNCH();
+                return MSS_OK;
+            }
             static std::atomic<bool> tc5_attr_set{false};
             if (!tc5_attr_set.load()) {
                 MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5_x4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM));

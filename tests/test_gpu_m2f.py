@@ -1,5 +1,5 @@
-"""flags: 0 = default fast path (TMA patch + tcgen05/TMEM 3xTF32 contraction), 4 = mma.sync contraction,
-2 = FP32-FMA contraction, 1 = generic any-resize kernel.
+"""flags: 0 = default fast path (TMA patch + tcgen05/TMEM 3xTF32 contraction, shared-tap 4x1 pixel blocks),
+8 = tcgen05 with one pixel per thread, 4 = mma.sync contraction, 2 = FP32-FMA contraction, 1 = generic any-resize kernel.
 
 GPU parity, Mask2Former post-head path: fused kernels vs outputs of the reference's own
 semantic_inference / get_anomaly_score bodies (tests/golden/scoring_golden.npz) and the torch oracle.
@@ -34,7 +34,7 @@ def close(got, want, rtol=RTOL, atol=ATOL):
     np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
 
 
-@pytest.mark.parametrize("flags", [0, 4, 2, 1], ids=["tma_tcgen05", "tma_mmasync", "tma_ffma", "generic"])
+@pytest.mark.parametrize("flags", [0, 8, 4, 2, 1], ids=["tma_tcgen05", "tma_tcgen05_pixel", "tma_mmasync", "tma_ffma", "generic"])
 def test_fused_from_lowres_golden(m2f, flags):
     cls, lo = D["m2f_cls"].cuda(), D["m2f_mask_lo"].cuda()
     outs = m2f.post_head_inference(cls, lo, (32, 64), flags=flags)
@@ -52,7 +52,7 @@ def test_dropin_signatures_on_upsampled_masks(m2f):
     close(got, G["m2f_anomaly"])
 
 
-@pytest.mark.parametrize("flags", [0, 4, 2, 1], ids=["tma_tcgen05", "tma_mmasync", "tma_ffma", "generic"])
+@pytest.mark.parametrize("flags", [0, 8, 4, 2, 1], ids=["tma_tcgen05", "tma_tcgen05_pixel", "tma_mmasync", "tma_ffma", "generic"])
 @pytest.mark.parametrize("hw,crop", [((64, 128), (256, 512)), ((68, 120), (270, 480)), ((36, 40), (141, 157))])
 def test_random_vs_oracle(m2f, flags, hw, crop):
     g = torch.Generator().manual_seed(hw[0] * 1000 + hw[1])
@@ -103,6 +103,8 @@ def test_full_resolution_tile_consistency(m2f):
     b = m2f.anomaly_score_from_lowres(cls, lo, (1024, 2048), (1024, 2048), flags=1)
     c = m2f.anomaly_score_from_lowres(cls, lo, (1024, 2048), (1024, 2048), flags=2)
     d = m2f.anomaly_score_from_lowres(cls, lo, (1024, 2048), (1024, 2048), flags=4)
+    e = m2f.anomaly_score_from_lowres(cls, lo, (1024, 2048), (1024, 2048), flags=8)
+    assert torch.allclose(e, b, rtol=RTOL, atol=ATOL)
     assert torch.allclose(a, b, rtol=RTOL, atol=ATOL)
     assert torch.allclose(c, b, rtol=RTOL, atol=ATOL)
     assert torch.allclose(d, b, rtol=RTOL, atol=ATOL)
