@@ -421,7 +421,7 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
     EncodeTiledFn enc = x4 ? get_encode_fn() : nullptr;
     const bool use_mma = x4 && enc && !(flags & MSS_M2F_FORCE_FFMA) && Q <= MM_QPAD - 4;
     const bool use_tc5 = use_mma && !(flags & MSS_M2F_FORCE_MMASYNC);
-    const bool use_tc5q = use_tc5 && !(flags & MSS_M2F_FORCE_TC5_PIXEL);
+    const bool use_tc5q = use_tc5 && !(flags & MSS_M2F_FORCE_TC5_PIXEL) && (Q % 4 == 0);
     if (x4 && enc) {
         CUtensorMap tmap;
         cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(B * Q)};
@@ -442,19 +442,26 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
             m2f_class_probs_umma_kernel<<<(unsigned)((B * T5_K + 127) / 128), 128, 0, st>>>(cls_logits, (int)B, Q, C + 1, p_hi, p_lo);
             MSS_CHECK_LAUNCH();
             if (use_tc5q) {
+                // debug switch: MSS_M2F_DUP_B=1 keeps two copies of each class-table core matrix instead of LBO = 0
+                static const bool dup_b = [] { const char *e = getenv("MSS_M2F_DUP_B"); return e && e[0] == '1'; }();
                 static std::atomic<bool> tq_attr_set{false};
                 if (!tq_attr_set.load()) {
-                    MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TQ_SMEM));
-                    MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TQ_SMEM));
+                    MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tq_smem(false)));
+                    MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tq_smem(false)));
+                    MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tq_smem(true)));
+                    MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tq_smem(true)));
                     tq_attr_set.store(true);
                 }
                 // blocks of 4 pixels start at x = 2 (mod 4): CTA bx covers x in [64 bx - 2, 64 bx + 62)
                 dim3 grid((Wc + 2 + TQ_W - 1) / TQ_W, (Hc + TQ_H - 1) / TQ_H, (unsigned)B);
                 MSS_REQUIRE(grid.y <= 65535, "mss_m2f_semantic_inference: grid too large");
-                if (has_extra)
-                    m2f_tc5q_kernel<true><<<grid, TQ_THREADS, TQ_SMEM, st>>>(tmap, p_hi, p_lo, Q, h, w, out);
-                else
-                    m2f_tc5q_kernel<false><<<grid, TQ_THREADS, TQ_SMEM, st>>>(tmap, p_hi, p_lo, Q, h, w, out);
+                if (dup_b) {
+                    if (has_extra) m2f_tc5q_kernel<true, true><<<grid, TQ_THREADS, tq_smem(true), st>>>(tmap, p_hi, p_lo, Q, h, w, out);
+                    else m2f_tc5q_kernel<false, true><<<grid, TQ_THREADS, tq_smem(true), st>>>(tmap, p_hi, p_lo, Q, h, w, out);
+                } else {
+                    if (has_extra) m2f_tc5q_kernel<true, false><<<grid, TQ_THREADS, tq_smem(false), st>>>(tmap, p_hi, p_lo, Q, h, w, out);
+                    else m2f_tc5q_kernel<false, false><<<grid, TQ_THREADS, tq_smem(false), st>>>(tmap, p_hi, p_lo, Q, h, w, out);
+                }
                 MSS_CHECK_LAUNCH();
                 return MSS_OK;
             }

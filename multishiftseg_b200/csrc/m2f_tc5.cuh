@@ -47,6 +47,20 @@ constexpr size_t T5_SMEM = (size_t)T5_PATCH_BYTES + 2 * T5_B_FLOATS * 4 + 128 * 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one elected lane of a converged warp.  Code under `if (elect_one_sync())` keeps its warp-uniform operands in
+// uniform registers; under `if (lane == 0)` the compiler wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY waterfall loop (~100 cycles per MMA, measured round 1).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %2;\n\t"
+        "@%%px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, %%rx;\n\t}"
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_commit(uint64_t *bar) {
@@ -288,20 +302,21 @@ m2f_tc5_x4_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restr
     } else {
         // ===== MMA issuer: the whole warp waits (stays converged), lane 0 issues =====
         const uint32_t bhi = smem_u32(s_bhi), blo = smem_u32(s_blo);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);           // warp-uniform copy for the MMA operands
         for (int t = 0; t < n_tiles; t++) {
             for (int s = 0; s < T5_STAGES; s++) {
                 mbar_wait(&bar_full[s], t & 1);
                 if (s == 0 && t > 0) mbar_wait(bar_dempty, (t - 1) & 1);  // epilogue has read the previous tile
                 tc5_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const int nks = (s == T5_STAGES - 1) ? 1 : 2;         // 104 = 6 x 16 + 8
                     for (int kk = 0; kk < nks; kk++) {
                         const int ks = 2 * s + kk;
                         const uint64_t dh = tc5_smem_desc(bhi + ks * 2 * (T5_N * 16), T5_N * 16, 128);
                         const uint64_t dl = tc5_smem_desc(blo + ks * 2 * (T5_N * 16), T5_N * 16, 128);
-                        tc5_mma_ts(tmem + T5_COL_D, tmem + T5_COL_ALO + ks * 8, dh, T5_IDESC, ks > 0);
-                        tc5_mma_ts(tmem + T5_COL_D, tmem + T5_COL_AHI + ks * 8, dl, T5_IDESC, 1);
-                        tc5_mma_ts(tmem + T5_COL_D, tmem + T5_COL_AHI + ks * 8, dh, T5_IDESC, 1);
+                        tc5_mma_ts(tmem_u + T5_COL_D, tmem_u + T5_COL_ALO + ks * 8, dh, T5_IDESC, ks > 0);
+                        tc5_mma_ts(tmem_u + T5_COL_D, tmem_u + T5_COL_AHI + ks * 8, dl, T5_IDESC, 1);
+                        tc5_mma_ts(tmem_u + T5_COL_D, tmem_u + T5_COL_AHI + ks * 8, dh, T5_IDESC, 1);
                     }
                     tc5_commit(&bar_empty[s]);
                     if (s == T5_STAGES - 1) tc5_commit(bar_dfull);

@@ -11,35 +11,47 @@
 //
 // A thread <-> one TMEM lane, so its 4 pixels go to 4 DIFFERENT M-tiles that are in flight together:
 //   M-tile i (i = 0..3) = pixel i of each of 128 blocks;  a "group" = 128 blocks = 8 rows x 64 px.
-//   CTA = 64 x 16 output pixels (x from 64*bx - 2: blocks start at x = 2 mod 4) = 2 groups, one TMA box
-//   (20 x 6 x 104 fp32, 49.9 KB) with the low-res patch of ALL queries; out-of-image halo cells are
+//   CTA = 64 x 32 output pixels (x from 64*bx - 2: blocks start at x = 2 mod 4) = 4 groups, one TMA box
+//   (20 x 10 x 104 fp32, 83.2 KB) with the low-res patch of ALL queries; out-of-image halo cells are
 //   overwritten with the edge value (torch clamps source indices), after which every tap is border-free.
-//   The contraction  semseg[px, c] = sum_q S[px, q] P[q, c]  is the same 3xTF32 split GEMM as before
-//   (S = S_hi + S_lo, P = P_hi + P_lo; D = S_lo*P_hi + S_hi*P_lo + S_hi*P_hi, fp32 accumulate in TMEM).
-//   * warps 0-7 (producers): warp = (lane quarter, half); per K-step of 8 queries a thread evaluates 4 queries
-//     (its half) x 4 pixels and writes S_hi / S_lo straight into TENSOR MEMORY (tcgen05.st 32x32b.x4) as the
-//     A operands of the 4 tiles; two A buffers alternate;
-//   * warp 8, one lane: per K-step 4 tiles x 3 tcgen05.mma (M = 128, N = 32, K = 8, A from TMEM, B = class-
+//   The contraction  semseg[px, c] = sum_q S[px, q] P[q, c]  is a split-TF32 GEMM with fp32 accumulation in
+//   TMEM: S = S_hi + S_lo, P = P_hi + P_lo (hi = top 19 bits, lo = exact remainder).  One K = 8 instruction
+//   covers FOUR queries: its A columns are [S_hi(q..q+3) | S_lo(q..q+3)] -- exactly what one thread produces,
+//   one 8-column tcgen05.st -- and it is issued twice, against B = [P_hi ; P_hi] and B = [P_lo ; P_lo]
+//   (the same 4-query core matrix for both K chunks: descriptor LBO = 0, or a duplicated table), which sums
+//   all four partial products (S_hi + S_lo)(P_hi + P_lo).
+//   * warps 0-7 (producers): warp = (lane quarter, half); per stage of 8 queries a thread evaluates 4 queries
+//     (its half) x 4 pixels and writes them straight into TENSOR MEMORY as the A operands of the 4 tiles; two
+//     A buffers alternate;
+//   * warp 8, one lane: per stage 4 tiles x 4 tcgen05.mma (M = 128, N = 32, K = 8, A from TMEM, B = class-
 //     probability table in shared memory), tcgen05.commit frees the A buffer / publishes the accumulators;
-//   * epilogue (all producer warps, after each group): tcgen05.ld of the accumulators; half h of a quarter
+//   * a producer evaluates its stage BEFORE waiting for the A buffer to be free, so the MMAs of two stages
+//     ago have a whole stage of slack;
+//   * epilogue (all producer warps, one stage into the next group so the last MMAs are long done): tcgen05.ld of the accumulators; half h of a quarter
 //     takes pixels 2h, 2h+1 of each block, so every class is one 8-byte store per thread and a warp writes
 //     contiguous 256-byte runs; 1 - max_c for the anomaly map.
-// TMEM: D tiles at columns 0..127, A buffers at 128..255 (per buffer: tile i hi at i*16, lo at i*16 + 8)
+// TMEM: D tiles at columns 0..127, A buffers at 128..255 (per buffer: tile i, half h at i*16 + 8*h)
 //   -> 256 columns per CTA, two CTAs per SM.
 #pragma once
 
+#ifndef TQ_EXPERIMENT
+#define TQ_EXPERIMENT 0     /* 1..3: timing experiments (wrong results), see scratch/gpu_m2f_exp.sh */
+#endif
+
 namespace mss {
 
-constexpr int TQ_W = 64, TQ_H = 16, TQ_GROUP_H = 8, TQ_GROUPS = 2;
-constexpr int TQ_BOX_W = 20, TQ_BOX_H = 6, TQ_BOX_X0 = 4;      // patch origin = (16*bx - 4, 4*by - 1)
+constexpr int TQ_W = 64, TQ_H = 32, TQ_GROUP_H = 8, TQ_GROUPS = 4;
+constexpr int TQ_BOX_W = 20, TQ_BOX_H = TQ_H / 4 + 2, TQ_BOX_X0 = 4;   // patch origin = (16*bx - 4, (TQ_H/4)*by - 1)
 constexpr int TQ_KSTEPS = T5_K / 8;                            // 13
-constexpr int TQ_QSTRIDE = TQ_BOX_W * TQ_BOX_H;                // 120 floats
-constexpr int TQ_PATCH_FLOATS = TQ_QSTRIDE * T5_K;             // 12480
-constexpr int TQ_PATCH_BYTES = TQ_PATCH_FLOATS * 4;            // 49920
+constexpr int TQ_QSTRIDE = TQ_BOX_W * TQ_BOX_H;                // 200 floats
+constexpr int TQ_PATCH_FLOATS = TQ_QSTRIDE * T5_K;             // 20800
+constexpr int TQ_PATCH_BYTES = TQ_PATCH_FLOATS * 4;            // 83200
 constexpr int TQ_TMEM_COLS = 256;
 constexpr int TQ_COL_D = 0, TQ_COL_A = 128;                    // D tile i: i*32; A buffer s: 128 + 64*s
 constexpr int TQ_THREADS = 288, TQ_PRODUCERS = 256;
-constexpr size_t TQ_SMEM = (size_t)TQ_PATCH_BYTES + 2 * T5_B_FLOATS * 4 + 128 * 8 + 16 * 8 + 16 + 128;
+constexpr size_t tq_smem(bool dup) {
+    return (size_t)TQ_PATCH_BYTES + (dup ? 4 : 2) * T5_B_FLOATS * 4 + 128 * 8 + 16 * 8 + 16 + 128;
+}
 
 __device__ __forceinline__ void tc5_st4(uint32_t taddr, const uint32_t (&v)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
@@ -56,15 +68,18 @@ __device__ __forceinline__ void stg_stream_f2(float *p, float a, float b) {
     asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
-template <bool HAS_EXTRA>
+// DUP_B: keep two copies of every 4-query core matrix of the class table in shared memory (K chunk 0 and 1)
+// instead of pointing both K chunks of the descriptor at the same one (LBO = 0)
+template <bool HAS_EXTRA, bool DUP_B>
 __global__ void __launch_bounds__(TQ_THREADS, 2)
 m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ p_hi,
                 const float *__restrict__ p_lo, int Q, int h, int w, M2FOut out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *s_patch = reinterpret_cast<float *>(smem_raw);                      // [104][6][20]
-    float *s_bhi = s_patch + TQ_PATCH_FLOATS;                                  // [26][32][4]
-    float *s_blo = s_bhi + T5_B_FLOATS;
-    int *s_keep = reinterpret_cast<int *>(s_blo + T5_B_FLOATS);                // [128]
+    float *s_patch = reinterpret_cast<float *>(smem_raw);                      // [104][10][20]
+    constexpr int BF = (DUP_B ? 2 : 1) * T5_B_FLOATS;
+    float *s_bhi = s_patch + TQ_PATCH_FLOATS;                                  // [26][1 or 2][32][4]
+    float *s_blo = s_bhi + BF;
+    int *s_keep = reinterpret_cast<int *>(s_blo + BF);                         // [128]
     float *s_kscore = reinterpret_cast<float *>(s_keep + 128);                 // [128]
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_kscore + 128);            // full[2] empty[2] d_full d_empty patch
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 16);
@@ -104,8 +119,15 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
         const float4 *gh = reinterpret_cast<const float4 *>(p_hi + (long long)b * T5_B_FLOATS);
         const float4 *gl = reinterpret_cast<const float4 *>(p_lo + (long long)b * T5_B_FLOATS);
         for (int i = tid; i < T5_B_FLOATS / 4; i += TQ_THREADS) {
-            reinterpret_cast<float4 *>(s_bhi)[i] = __ldg(gh + i);
-            reinterpret_cast<float4 *>(s_blo)[i] = __ldg(gl + i);
+            const float4 vh = __ldg(gh + i), vl = __ldg(gl + i);
+            if (DUP_B) {
+                const int o = (i >> 5) * 64 + (i & 31);                        // chunk k' -> [k'][0][c], [k'][1][c]
+                reinterpret_cast<float4 *>(s_bhi)[o] = vh; reinterpret_cast<float4 *>(s_bhi)[o + 32] = vh;
+                reinterpret_cast<float4 *>(s_blo)[o] = vl; reinterpret_cast<float4 *>(s_blo)[o + 32] = vl;
+            } else {
+                reinterpret_cast<float4 *>(s_bhi)[i] = vh;
+                reinterpret_cast<float4 *>(s_blo)[i] = vl;
+            }
         }
         if (HAS_EXTRA)
             for (int i = tid; i < 128; i += TQ_THREADS) {
@@ -140,60 +162,9 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
         const float *tap_col = s_patch + (jb + TQ_BOX_X0 - 1);      // column k = 16*bx + jb - 1 of the patch
         const bool vec2 = ((out.Wc & 1) == 0);
 
-        for (int g = 0; g < n_groups; g++) {
-            const int yy = g * TQ_GROUP_H + rowg;                   // row inside the CTA block
-            const int y = y_block + yy;
-            float wy1;
-            {
-                const float sy = 0.25f * ((float)(yy & 3) + 0.5f) - 0.5f;
-                wy1 = sy - floorf(sy);
-            }
-            const int r_off = ((yy - 2) >> 2) + 1;                  // upper tap row in the patch
-            const float *tap = tap_col + r_off * TQ_BOX_W + half * 4 * TQ_QSTRIDE;
-
-            for (int ks = 0; ks < TQ_KSTEPS; ks++, tap += 8 * TQ_QSTRIDE) {
-                const int u = g * TQ_KSTEPS + ks, slot = u & 1;
-                if (u >= 2) mbar_wait(&bar_empty[slot], ((u >> 1) + 1) & 1);   // MMAs of use u-2 have read this buffer
-                tc5_fence_after();
-                const int q0 = ks * 8 + half * 4;
-                uint32_t hi[4][4], lo[4][4];                        // [pixel / tile][query]
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float *p = tap + j * TQ_QSTRIDE;
-                    const float a = p[0], bb = p[1], c = p[TQ_BOX_W], d = p[TQ_BOX_W + 1];
-                    const float L = fmaf(wy1, c - a, a), R = fmaf(wy1, d - bb, bb);
-                    const float D = R - L, Ls = NL2E * L;
-                    float e[4] = {fmaf(wxs0, D, Ls), fmaf(wxs1, D, Ls), fmaf(wxs2, D, Ls), fmaf(wxs3, D, Ls)};
-                    const bool live = q0 + j < Q;                   // padded queries (>= Q) belong to the next image
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        float ex, sg;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(e[i]));
-                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex));
-                        if (!live) sg = 0.f;
-                        hi[i][j] = __float_as_uint(sg) & 0xFFFFE000u;
-                        lo[i][j] = __float_as_uint(sg - __uint_as_float(hi[i][j]));
-                        if (HAS_EXTRA) {
-                            const int slot_k = s_keep[q0 + j];
-                            const int x = xb + i;
-                            if (slot_k >= 0 && x >= 0 && x < out.Wc && y < out.Hc)
-                                out.extra[(long long)b * out.extra_bstride + (long long)slot_k * plane + (long long)y * out.Wc + x] =
-                                    s_kscore[q0 + j] * sg;
-                        }
-                    }
-                }
-                const uint32_t a_base = lane_base + TQ_COL_A + slot * 64 + half * 4;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    tc5_st4(a_base + i * 16, hi[i]);
-                    tc5_st4(a_base + i * 16 + 8, lo[i]);
-                }
-                tc5_wait_st();
-                tc5_fence_before();
-                mbar_arrive(&bar_full[slot]);
-            }
-
-            // ----- epilogue of this group: half h stores pixels 2h, 2h+1 of every block -----
+        // epilogue of group g: half h stores pixels 2h, 2h+1 of every block
+        auto epilogue = [&](int g) {
+            const int y = y_block + g * TQ_GROUP_H + rowg;
             mbar_wait(bar_dfull, g & 1);
             tc5_fence_after();
             const int x0 = xb + 2 * half;
@@ -236,25 +207,107 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                     if (ok1) stg_stream_f1(pa + 1, 1.0f - mx1);
                 }
             }
+        };
+
+        for (int g = 0; g < n_groups; g++) {
+            const int yy = g * TQ_GROUP_H + rowg;                   // row inside the CTA block
+            const int y = y_block + yy;
+            float wy1;
+            {
+                const float sy = 0.25f * ((float)(yy & 3) + 0.5f) - 0.5f;
+                wy1 = sy - floorf(sy);
+            }
+            const int r_off = ((yy - 2) >> 2) + 1;                  // upper tap row in the patch
+            const float *tap = tap_col + r_off * TQ_BOX_W + half * 4 * TQ_QSTRIDE;
+
+            for (int ks = 0; ks < TQ_KSTEPS; ks++, tap += 8 * TQ_QSTRIDE) {
+                const int u = g * TQ_KSTEPS + ks, slot = u & 1;
+                const int q0 = ks * 8 + half * 4;
+                const uint32_t a_base = lane_base + TQ_COL_A + slot * 64 + half * 8;
+                if (q0 < Q) {                                       // Q % 4 == 0 on this path (host-checked)
+                    uint32_t v[4][8];                               // [pixel / tile][hi q0..q0+3 | lo q0..q0+3]
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const float *p = tap + j * TQ_QSTRIDE;
+                        const float a = p[0], bb = p[1], c = p[TQ_BOX_W], d = p[TQ_BOX_W + 1];
+                        const float L = fmaf(wy1, c - a, a), R = fmaf(wy1, d - bb, bb);
+                        const float D = R - L, Ls = NL2E * L;
+                        float e[4] = {fmaf(wxs0, D, Ls), fmaf(wxs1, D, Ls), fmaf(wxs2, D, Ls), fmaf(wxs3, D, Ls)};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            float ex, sg;
+#if TQ_EXPERIMENT == 1      /* timing experiment: no MUFU */
+                            ex = e[i] * e[i]; sg = fmaf(ex, 0.25f, 0.5f);
+#else
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(e[i]));
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex));
+#endif
+                            v[i][j] = __float_as_uint(sg) & 0xFFFFE000u;
+                            v[i][4 + j] = __float_as_uint(sg - __uint_as_float(v[i][j]));
+                            if (HAS_EXTRA) {
+                                const int slot_k = s_keep[q0 + j];
+                                const int x = xb + i;
+                                if (slot_k >= 0 && x >= 0 && x < out.Wc && y < out.Hc)
+                                    out.extra[(long long)b * out.extra_bstride + (long long)slot_k * plane + (long long)y * out.Wc + x] =
+                                        s_kscore[q0 + j] * sg;
+                            }
+                        }
+                    }
+                    // the values are ready: only now wait for the MMAs of use u-2 to have read this A buffer
+                    if (u >= 2) mbar_wait(&bar_empty[slot], ((u >> 1) + 1) & 1);
+                    tc5_fence_after();
+#if TQ_EXPERIMENT == 2      /* timing experiment: one TMEM store instead of four */
+                    { uint32_t w8[8];
+#pragma unroll
+                      for (int k = 0; k < 8; k++) w8[k] = v[0][k] ^ v[1][k] ^ v[2][k] ^ v[3][k];
+                      tc5_st8(a_base, w8); }
+#else
+#pragma unroll
+                    for (int i = 0; i < 4; i++) tc5_st8(a_base + i * 16, v[i]);
+#endif
+                } else {
+                    // padded queries: the box holds the next image's masks there; they must not reach the MMA
+                    if (u >= 2) mbar_wait(&bar_empty[slot], ((u >> 1) + 1) & 1);
+                    tc5_fence_after();
+                    const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) tc5_st8(a_base + i * 16, z);
+                }
+                tc5_wait_st();
+                tc5_fence_before();
+                mbar_arrive(&bar_full[slot]);
+                // epilogue of the previous group, one stage late: its last MMAs have had a whole stage to finish
+                if (ks == 0 && g > 0) epilogue(g - 1);
+            }
         }
+        epilogue(n_groups - 1);
     } else {
         // ===== MMA issuer: the whole warp waits (stays converged), lane 0 issues =====
         const uint32_t bhi = smem_u32(s_bhi), blo = smem_u32(s_blo);
+        // warp-uniform copy of the TMEM base + elect_one_sync() below: tcgen05.mma takes its operands from uniform
+        // registers; with a per-thread base under `if (lane == 0)` every MMA sat in an ELECT / R2UR.BROADCAST /
+        // BRA.U.ANY waterfall loop (~100 cycles per MMA), which made MMA issue the critical path of the kernel
+        // (ncu + timing experiments, round 1)
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
         for (int g = 0; g < n_groups; g++) {
             for (int ks = 0; ks < TQ_KSTEPS; ks++) {
                 const int u = g * TQ_KSTEPS + ks, slot = u & 1;
                 mbar_wait(&bar_full[slot], (u >> 1) & 1);
                 if (ks == 0 && g > 0) mbar_wait(bar_dempty, (g - 1) & 1);     // epilogue has read the previous group
                 tc5_fence_after();
-                if (lane == 0) {
-                    const uint64_t dh = tc5_smem_desc(bhi + ks * 2 * (T5_N * 16), T5_N * 16, 128);
-                    const uint64_t dl = tc5_smem_desc(blo + ks * 2 * (T5_N * 16), T5_N * 16, 128);
+                if (elect_one_sync()) {
+                    // 4-query core matrix k' = 2 ks + hh of the class table, used for both K chunks
+                    constexpr uint32_t CHUNK = T5_N * 16 * (DUP_B ? 2 : 1), LBO = DUP_B ? T5_N * 16 : 0;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const uint32_t d = tmem + TQ_COL_D + i * 32, a = tmem + TQ_COL_A + slot * 64 + i * 16;
-                        tc5_mma_ts(d, a + 8, dh, T5_IDESC, ks > 0);
-                        tc5_mma_ts(d, a, dl, T5_IDESC, 1);
-                        tc5_mma_ts(d, a, dh, T5_IDESC, 1);
+                    for (int hh = 0; hh < 2; hh++) {
+                        const uint64_t dh = tc5_smem_desc(bhi + (2 * ks + hh) * CHUNK, LBO, 128);
+                        const uint64_t dl = tc5_smem_desc(blo + (2 * ks + hh) * CHUNK, LBO, 128);
+#pragma unroll
+                        for (int i = 0; i < (TQ_EXPERIMENT == 3 ? 1 : 4); i++) {      /* experiment 3: a quarter of the MMAs */
+                            const uint32_t d = tmem_u + TQ_COL_D + i * 32, a = tmem_u + TQ_COL_A + slot * 64 + i * 16 + hh * 8;
+                            tc5_mma_ts(d, a, dh, T5_IDESC, (ks | hh) > 0);
+                            tc5_mma_ts(d, a, dl, T5_IDESC, 1);
+                        }
                     }
                     tc5_commit(&bar_empty[slot]);
                     if (ks == TQ_KSTEPS - 1) tc5_commit(bar_dfull);
