@@ -129,6 +129,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// same, for a warp that has nothing else to do (the MMA issuer): back off between polls so the spin does not
+// take issue slots from the warps doing the arithmetic
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, unsigned parity, unsigned ns) {
+    for (;;) {
+        unsigned done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
 // 1-D bulk copy global -> shared (TMA engine, no tensor map): src/dst 16-byte aligned, bytes % 16 == 0;
 // completion is signalled on `bar` as transaction bytes
 __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {

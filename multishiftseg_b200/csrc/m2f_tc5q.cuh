@@ -70,6 +70,23 @@ __device__ __forceinline__ void stg_stream_f2(float *p, float a, float b) {
 
 // DUP_B: keep two copies of every 4-query core matrix of the class table in shared memory (K chunk 0 and 1)
 // instead of pointing both K chunks of the descriptor at the same one (LBO = 0)
+// 1 / d for d in [1, 2^127) on the FMA pipe: integer-subtract seed (|1 - d y0| <= 0.0506), one cubic and one
+// quadratic Newton step (error 0.0506^3 -> squared = 1.7e-8, below float32 rounding).  Used for TQ_RCP_FMA of
+// the 4 pixels of a block to take load off the MUFU pipe, which binds this kernel (timing experiments, round 1:
+// dropping either MUFU of the sigmoid took 146 -> 118 us/image).
+#ifndef TQ_RCP_FMA
+#define TQ_RCP_FMA 0     /* measured: 0 -> 145.1, 1 -> 148.2, 2 -> 147.2, 3 -> 151.5 us/image (issue slots co-limit) */
+#endif
+#ifndef TQ_MMA_SLEEP_NS
+#define TQ_MMA_SLEEP_NS 32
+#endif
+__device__ __forceinline__ float rcp_fma(float d) {
+    const float y0 = __int_as_float(0x7EF31000 - __float_as_int(d));
+    const float r = fmaf(-d, y0, 1.0f);
+    const float y1 = fmaf(y0, fmaf(r, r, r), y0);
+    return fmaf(y1, fmaf(-d, y1, 1.0f), y1);
+}
+
 template <bool HAS_EXTRA, bool DUP_B>
 __global__ void __launch_bounds__(TQ_THREADS, 2)
 m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ p_hi,
@@ -226,30 +243,50 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                 const uint32_t a_base = lane_base + TQ_COL_A + slot * 64 + half * 8;
                 if (q0 < Q) {                                       // Q % 4 == 0 on this path (host-checked)
                     uint32_t v[4][8];                               // [pixel / tile][hi q0..q0+3 | lo q0..q0+3]
+                    // Software pipeline over the 4 queries: the ex2 of query j are issued together with the rcp of
+                    // query j-1 (volatile asm keeps that order), so a warp offers the MUFU pipe -- the binding pipe,
+                    // 8 issue cycles per warp instruction -- a steady trickle instead of bursts of 16 + 16.
+                    float ex[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float *p = tap + j * TQ_QSTRIDE;
-                        const float a = p[0], bb = p[1], c = p[TQ_BOX_W], d = p[TQ_BOX_W + 1];
-                        const float L = fmaf(wy1, c - a, a), R = fmaf(wy1, d - bb, bb);
-                        const float D = R - L, Ls = NL2E * L;
-                        float e[4] = {fmaf(wxs0, D, Ls), fmaf(wxs1, D, Ls), fmaf(wxs2, D, Ls), fmaf(wxs3, D, Ls)};
+                    for (int j = 0; j <= 4; j++) {
+                        float e[4];
+                        if (j < 4) {
+                            const float *p = tap + j * TQ_QSTRIDE;
+                            const float a = p[0], bb = p[1], c = p[TQ_BOX_W], d = p[TQ_BOX_W + 1];
+                            const float L = fmaf(wy1, c - a, a), R = fmaf(wy1, d - bb, bb);
+                            const float D = R - L, Ls = NL2E * L;
+                            e[0] = fmaf(wxs0, D, Ls); e[1] = fmaf(wxs1, D, Ls); e[2] = fmaf(wxs2, D, Ls); e[3] = fmaf(wxs3, D, Ls);
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            float ex, sg;
-#if TQ_EXPERIMENT == 1      /* timing experiment: no MUFU */
-                            ex = e[i] * e[i]; sg = fmaf(ex, 0.25f, 0.5f);
+                            float sg = 0.f;
+                            if (j > 0) {
+#if TQ_EXPERIMENT == 1 || TQ_EXPERIMENT == 4     /* timing experiment: no MUFU / no rcp */
+                                sg = fmaf(ex[i], 0.25f, 0.5f);
 #else
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(e[i]));
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex));
+                                if (i < TQ_RCP_FMA) sg = rcp_fma(1.0f + ex[i]);
+                                else asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex[i]));
 #endif
-                            v[i][j] = __float_as_uint(sg) & 0xFFFFE000u;
-                            v[i][4 + j] = __float_as_uint(sg - __uint_as_float(v[i][j]));
-                            if (HAS_EXTRA) {
-                                const int slot_k = s_keep[q0 + j];
-                                const int x = xb + i;
-                                if (slot_k >= 0 && x >= 0 && x < out.Wc && y < out.Hc)
-                                    out.extra[(long long)b * out.extra_bstride + (long long)slot_k * plane + (long long)y * out.Wc + x] =
-                                        s_kscore[q0 + j] * sg;
+                            }
+                            if (j < 4) {
+#if TQ_EXPERIMENT == 1 || TQ_EXPERIMENT == 5     /* no MUFU / no ex2 */
+                                ex[i] = e[i] * e[i];
+#else
+                                // (the FMA-pipe reciprocal needs a finite 1 + 2^e: clamp e, i.e. mask logits below -87)
+                                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex[i]) : "f"(i < TQ_RCP_FMA ? fminf(e[i], 126.f) : e[i]));
+#endif
+                            }
+                            if (j > 0) {
+                                const int jq = j - 1;
+                                v[i][jq] = __float_as_uint(sg) & 0xFFFFE000u;
+                                v[i][4 + jq] = __float_as_uint(sg - __uint_as_float(v[i][jq]));
+                                if (HAS_EXTRA) {
+                                    const int slot_k = s_keep[q0 + jq];
+                                    const int x = xb + i;
+                                    if (slot_k >= 0 && x >= 0 && x < out.Wc && y < out.Hc)
+                                        out.extra[(long long)b * out.extra_bstride + (long long)slot_k * plane + (long long)y * out.Wc + x] =
+                                            s_kscore[q0 + jq] * sg;
+                                }
                             }
                         }
                     }
@@ -292,8 +329,8 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
         for (int g = 0; g < n_groups; g++) {
             for (int ks = 0; ks < TQ_KSTEPS; ks++) {
                 const int u = g * TQ_KSTEPS + ks, slot = u & 1;
-                mbar_wait(&bar_full[slot], (u >> 1) & 1);
-                if (ks == 0 && g > 0) mbar_wait(bar_dempty, (g - 1) & 1);     // epilogue has read the previous group
+                mbar_wait_backoff(&bar_full[slot], (u >> 1) & 1, TQ_MMA_SLEEP_NS);
+                if (ks == 0 && g > 0) mbar_wait_backoff(bar_dempty, (g - 1) & 1, TQ_MMA_SLEEP_NS);   // epilogue has read the previous group
                 tc5_fence_after();
                 if (elect_one_sync()) {
                     // 4-query core matrix k' = 2 ks + hh of the class table, used for both K chunks
