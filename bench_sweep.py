@@ -140,7 +140,8 @@ def main():
         }
         if world > 1 and getattr(ev, "last_exchange", None):
             x = ev.last_exchange
-            line["exchange"] = {"recv_pairs_rank0": int(sum(x["recv_counts"])), "thresholds_per_rank": x["thresholds_per_rank"]}
+            line["exchange"] = {"recv_pairs_rank0": int(sum(x["recv_counts"])), "thresholds_per_rank": x["thresholds_per_rank"],
+                                "phase_ms_rank0": {k: round(v, 3) for k, v in x.get("phase_ms", {}).items()}}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

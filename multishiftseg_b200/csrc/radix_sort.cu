@@ -414,27 +414,86 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict_
         sweep_tile<DigitFn, false>(sm, keys_in, keys_out, vals_in, vals_out, n, bin_base, tile_status, digit_of, tile);
 }
 
-// top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536, global atomics after
-// per-warp aggregation; adjacent pixels of a score map tend to share high key bits)
-__global__ void __launch_bounds__(256)
-keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift, unsigned long long *hist) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long iters = (n + stride - 1) / stride;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536).
+// First form: warp-aggregated atomics straight to the global bins -- 465 ms for 2 G keys on B200 (cfg-4, two
+// ranks): real score distributions put most keys into a few hundred bins, and every SM hammered the same L2
+// addresses.  Now each CTA (one per SM) privatises a window of 32 768 bins in 128 KB of shared memory, walks its
+// contiguous chunk of keys once per window (two windows for 16 bits), and adds its non-zero bins to the global
+// histogram at the end of the window.  Inside a warp, groups of equal bins are peeled with ballots so that a
+// hot bin costs one shared-memory atomic per warp, not 32 serialised ones.
+constexpr int KH_THREADS = 512;
+constexpr int KH_WINDOW = 32768;
+constexpr int KH_SMEM = KH_WINDOW * 4;
+
+__device__ __forceinline__ void kh_add(unsigned *s_hist, unsigned b, bool valid) {
+    unsigned remaining = __ballot_sync(0xffffffffu, valid);
     const unsigned lane = lane_id();
-    for (long long it = 0; it < iters; it++, i += stride) {
-        const bool valid = i < n;
-        const unsigned b = valid ? (__ldg(keys + i) >> shift) : 0u;
-        unsigned remaining = __ballot_sync(0xffffffffu, valid);
-        // peel groups of equal bins (leader = lowest remaining lane); after 4 rounds fall back to plain atomics
-        for (int round = 0; round < 4 && remaining; round++) {
-            const int leader = __ffs(remaining) - 1;
-            const unsigned v = __shfl_sync(0xffffffffu, b, leader);
-            const unsigned m = __ballot_sync(0xffffffffu, valid && b == v) & remaining;
-            if ((int)lane == leader) atomicAdd(hist + v, (unsigned long long)__popc(m));
-            remaining &= ~m;
+#pragma unroll 1
+    for (int round = 0; round < 4 && remaining; round++) {
+        const int leader = __ffs(remaining) - 1;
+        const unsigned v = __shfl_sync(0xffffffffu, b, leader);
+        const unsigned m = __ballot_sync(0xffffffffu, valid && b == v) & remaining;
+        if ((int)lane == leader) atomicAdd(s_hist + v, (unsigned)__popc(m));
+        remaining &= ~m;
+    }
+    if ((remaining >> lane) & 1u) atomicAdd(s_hist + b, 1u);
+}
+
+__global__ void __launch_bounds__(KH_THREADS, 1)
+keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift, unsigned nbins,
+                      unsigned long long *__restrict__ hist) {
+    extern __shared__ __align__(16) unsigned s_hist[];
+    // contiguous chunk of whole uint4 groups per CTA; the <= 3 + 3 unaligned head / tail keys go to CTA 0
+    const long long head = min(n, (long long)(((16 - ((uintptr_t)keys & 15)) & 15) >> 2));
+    const long long groups4 = (n - head) >> 2;
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + head);
+    const long long per = (groups4 + gridDim.x - 1) / gridDim.x;
+    const long long g0 = min(groups4, (long long)blockIdx.x * per), g1 = min(groups4, g0 + per);
+    const long long iters = (g1 - g0 + KH_THREADS - 1) / KH_THREADS;          // uniform per CTA (ballots inside)
+    for (unsigned base = 0; base < nbins; base += KH_WINDOW) {
+        for (int i = threadIdx.x; i < KH_WINDOW; i += KH_THREADS) s_hist[i] = 0;
+        __syncthreads();
+        for (long long it = 0; it < iters; it++) {
+            const long long g = g0 + it * KH_THREADS + threadIdx.x;
+            const bool in = g < g1;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (in) v = __ldg(k4 + g);
+            const unsigned b0 = (v.x >> shift) - base, b1 = (v.y >> shift) - base, b2 = (v.z >> shift) - base,
+                           b3 = (v.w >> shift) - base;
+            // the lane's own four keys first: adjacent pixels usually share a bin
+            const bool same4 = b0 == b1 && b0 == b2 && b0 == b3;
+            if (__all_sync(0xffffffffu, same4 || !in)) {
+                // every lane holds four equal bins: one aggregation round with weight 4
+                const bool valid = in && b0 < (unsigned)KH_WINDOW;
+                unsigned remaining = __ballot_sync(0xffffffffu, valid);
+                const unsigned lane = lane_id();
+#pragma unroll 1
+                for (int round = 0; round < 4 && remaining; round++) {
+                    const int leader = __ffs(remaining) - 1;
+                    const unsigned vv = __shfl_sync(0xffffffffu, b0, leader);
+                    const unsigned m = __ballot_sync(0xffffffffu, valid && b0 == vv) & remaining;
+                    if ((int)lane == leader) atomicAdd(s_hist + vv, 4u * (unsigned)__popc(m));
+                    remaining &= ~m;
+                }
+                if ((remaining >> lane) & 1u) atomicAdd(s_hist + b0, 4u);
+            } else {
+                kh_add(s_hist, b0, in && b0 < (unsigned)KH_WINDOW);
+                kh_add(s_hist, b1, in && b1 < (unsigned)KH_WINDOW);
+                kh_add(s_hist, b2, in && b2 < (unsigned)KH_WINDOW);
+                kh_add(s_hist, b3, in && b3 < (unsigned)KH_WINDOW);
+            }
         }
-        if ((remaining >> lane) & 1u) atomicAdd(hist + b, 1ull);
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            for (long long i = 0; i < n; i++) {
+                if (i == head) i += groups4 << 2;
+                if (i >= n) break;
+                const unsigned b = (__ldg(keys + i) >> shift) - base;
+                if (b < (unsigned)KH_WINDOW) atomicAdd(s_hist + b, 1u);
+            }
+        __syncthreads();
+        for (int i = threadIdx.x; i < KH_WINDOW && base + i < nbins; i += KH_THREADS)
+            if (s_hist[i]) atomicAdd(hist + base + i, (unsigned long long)s_hist[i]);
+        __syncthreads();
     }
 }
 
@@ -529,8 +588,14 @@ extern "C" int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int
     MSS_CHECK_CUDA(cudaMemsetAsync(hist, 0, sizeof(int64_t) << bits, st));
     if (n == 0) return MSS_OK;
     MSS_REQUIRE(keys, "mss_keys_histogram: null keys");
-    int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
-    keys_histogram_kernel<<<grid, 256, 0, st>>>(keys, n, 32 - bits, (unsigned long long *)hist);
+    static std::atomic<bool> kh_attr{false};
+    if (!kh_attr.load()) {
+        MSS_CHECK_CUDA(cudaFuncSetAttribute(keys_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KH_SMEM));
+        kh_attr.store(true);
+    }
+    // one CTA per SM (128 KB window each); small inputs use fewer CTAs (>= 16 K keys per CTA)
+    int grid = (int)std::max<long long>(1, std::min<long long>((n + 16383) / 16384, (long long)sm_count()));
+    keys_histogram_kernel<<<grid, KH_THREADS, KH_SMEM, st>>>(keys, n, 32 - bits, 1u << bits, (unsigned long long *)hist);
     MSS_CHECK_LAUNCH();
     return MSS_OK;
 }
@@ -564,6 +629,38 @@ partition_count_tiles_kernel(const uint32_t *__restrict__ keys, long long n, Spl
     if (s_c[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_c[threadIdx.x]);
 }
 
+// parts <= 16 (one destination per GPU of a box): lane-private counters, no atomics in the loop.  The atomic
+// version above serialises 32-way when almost every key of a warp goes to the same destination.
+constexpr int PC_SMALL = 16;
+__global__ void __launch_bounds__(256)
+partition_count_small_kernel(const uint32_t *__restrict__ keys, long long n, SplitterDigit dg,
+                             unsigned long long *__restrict__ counts) {
+    __shared__ unsigned s_c[PC_SMALL * 256];
+    __shared__ uint32_t s_spl[PC_SMALL];
+#pragma unroll
+    for (int p = 0; p < PC_SMALL; p++) s_c[p * 256 + threadIdx.x] = 0;
+    if (threadIdx.x < PC_SMALL) s_spl[threadIdx.x] = ((int)threadIdx.x < dg.nspl) ? dg.spl[threadIdx.x] : 0xFFFFFFFFu;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = __ldg(keys + i);
+        unsigned d = 0;
+#pragma unroll
+        for (int j = 0; j < PC_SMALL - 1; j++) d += (j < dg.nspl && k >= s_spl[j]);   // dest = #{j : key >= spl[j]}
+        s_c[d * 256 + threadIdx.x]++;
+    }
+    __syncthreads();
+    // warp w sums destinations w, w + 8
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = warp; p < PC_SMALL; p += 8) {
+        unsigned long long acc = 0;
+        for (int t = lane; t < 256; t += 32) acc += s_c[p * 256 + t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && acc) atomicAdd(counts + p, acc);
+    }
+}
+
 extern "C" int mss_partition_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n, const uint32_t *splitters,
                                    int parts, uint32_t *keys_out, uint8_t *labs_out, int64_t *out_counts_host,
                                    void *workspace, size_t workspace_bytes, void *stream) {
@@ -587,7 +684,8 @@ extern "C" int mss_partition_pairs(const uint32_t *keys, const uint8_t *labs, in
     MSS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)((char *)(status + tiles * RADIX) - (char *)workspace), st));
     SplitterDigit dg{splitters, parts - 1};
     int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
-    partition_count_tiles_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
+    if (parts <= PC_SMALL) partition_count_small_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
+    else partition_count_tiles_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
     MSS_CHECK_LAUNCH();
     partition_bases_kernel<<<1, RADIX, 0, st>>>(counts, base);
     MSS_CHECK_LAUNCH();

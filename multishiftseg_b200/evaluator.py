@@ -167,9 +167,17 @@ class StreamingEvaluator:
         return self._compute_distributed(m, n_pos, nan, inf, recall_level)
 
     def _compute_distributed(self, m, n_pos, nan, inf, recall_level):
+        import time
         import torch.distributed as dist
         be, g = self.backend, self.group
         world, rank = dist.get_world_size(g), dist.get_rank(g)
+        # host wall clock per phase (every phase ends in a host-visible result, so it is synchronised)
+        marks = [("start", time.perf_counter())]
+
+        def mark(name):
+            if torch.cuda.is_available() and getattr(be, "device", None) is not None:
+                torch.cuda.synchronize(be.device)
+            marks.append((name, time.perf_counter()))
 
         # 1. global emptiness / finiteness decisions (identical on every rank)
         tot = be.tensor([m, n_pos, nan, inf], torch.int64)
@@ -178,15 +186,18 @@ class StreamingEvaluator:
         if P == 0 or P == M:
             return None
         _raise_nonfinite(gnan, ginf)
+        mark("counts_allreduce")
 
         # 2. global histogram of the top key bits -> splitters
         keys, labs = be.pairs(self.buf, m)
         hist = be.histogram(keys, m, HIST_BITS)
         dist.all_reduce(hist, group=g)
         splitters = choose_splitters(hist.cpu().numpy(), world)
+        mark("histogram_splitters")
 
         # 3. local partition by destination rank, exchange
         pk, pl, send_counts = be.partition(keys, labs, m, splitters, world)
+        mark("partition")
         cm = be.tensor(send_counts, torch.int64)
         all_counts = be.empty(world * world, torch.int64)
         dist.all_gather_into_tensor(all_counts, cm, group=g)
@@ -196,9 +207,11 @@ class StreamingEvaluator:
         rk, rl = be.empty(max(m2, 1), torch.int32), be.empty(max(m2, 1), torch.uint8)
         dist.all_to_all_single(rk[:m2], pk, recv_counts, send_counts, group=g)
         dist.all_to_all_single(rl[:m2], pl, recv_counts, send_counts, group=g)
+        mark("all_to_all")
 
         # 4. local sort + run-length counts with global prefixes
         be.sort(rk, rl, m2)
+        mark("sort")
         lp = int((rl[:m2] != 0).sum().item()) if m2 else 0
         mine = be.tensor([m2, lp], torch.int64)
         per_rank = be.empty(2 * world, torch.int64)
@@ -210,6 +223,7 @@ class StreamingEvaluator:
             tps, fps = be.counts(rk, rl, m2, pos_before, idx_before)
         else:
             tps, fps = be.empty(0, torch.int64), be.empty(0, torch.int64)
+        mark("counts")
 
         # 5. gather every rank's thresholds (padded to the longest slice), run the identical tail everywhere
         T = be.tensor([tps.numel()], torch.int64)
@@ -226,9 +240,13 @@ class StreamingEvaluator:
         gathered = gathered.view(world, 2, Tmax)
         tps_all = torch.cat([gathered[r, 0, : Ts[r]] for r in range(world)])
         fps_all = torch.cat([gathered[r, 1, : Ts[r]] for r in range(world)])
+        mark("gather_thresholds")
+        res = be.tail(tps_all, fps_all, recall_level)
+        mark("tail")
         self.last_exchange = {"send_counts": send_counts, "recv_counts": recv_counts, "splitters": splitters,
-                              "thresholds_per_rank": Ts}
-        return be.tail(tps_all, fps_all, recall_level)
+                              "thresholds_per_rank": Ts,
+                              "phase_ms": {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}}
+        return res
 
 
 def _raise_nonfinite(nan, inf):

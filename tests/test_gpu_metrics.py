@@ -202,6 +202,51 @@ def test_histogram_and_partition(M):
     assert np.array_equal(vo.cpu().numpy(), v[order])
 
 
+@pytest.mark.parametrize("bits", [16, 15, 12, 3])
+def test_keys_histogram_skewed_and_unaligned(M, bits):
+    """Score-like keys: almost everything in a few hundred bins (the case that made global atomics crawl),
+    runs of equal bins, an unaligned key pointer, sizes around the vector / chunk boundaries."""
+    from multishiftseg_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(bits)
+    st = torch.cuda.current_stream().cuda_stream
+    for n in [1, 3, 5, 4099, 700_001, 3_000_003]:
+        s = (rng.standard_normal(n + 1) * 2 - 3).astype(np.float32)
+        s[: n // 2] = np.repeat(s[: (n // 2 + 63) // 64], 64)[: n // 2]        # runs of 64 equal scores
+        u = s.view(np.uint32)
+        k = ~np.where(u >> 31, ~u, u | np.uint32(0x80000000))
+        kt = torch.from_numpy(k.view(np.int32)).cuda()[1:]                    # 4-byte aligned only
+        hist = torch.empty(1 << bits, dtype=torch.int64, device="cuda")
+        assert lib.mss_keys_histogram(kt.data_ptr(), n, bits, hist.data_ptr(), st) == 0
+        assert np.array_equal(hist.cpu().numpy(), np.bincount(k[1:] >> (32 - bits), minlength=1 << bits))
+
+
+@pytest.mark.parametrize("parts", [1, 2, 8, 16, 17, 200])
+def test_partition_many_and_few_parts(M, parts):
+    from multishiftseg_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(parts)
+    n = 777_777
+    k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    k[: n // 2] = (k[: n // 2] >> 12) | np.uint32(0x40000000)               # half the keys in a narrow range
+    v = rng.integers(0, 2, size=n, dtype=np.uint8)
+    spl = np.sort(rng.choice(k, size=parts - 1, replace=False)).astype(np.uint32) if parts > 1 else np.zeros(0, np.uint32)
+    kt, vt = torch.from_numpy(k.view(np.int32)).cuda(), torch.from_numpy(v).cuda()
+    splt = torch.from_numpy(np.concatenate([spl, np.zeros(1, np.uint32)]).view(np.int32)).cuda()
+    ko, vo = torch.empty_like(kt), torch.empty_like(vt)
+    nb = lib.mss_partition_workspace_bytes(n)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    counts = (C.c_int64 * parts)()
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.mss_partition_pairs(kt.data_ptr(), vt.data_ptr(), n, splt.data_ptr(), parts, ko.data_ptr(), vo.data_ptr(),
+                                   counts, ws.data_ptr(), nb, st) == 0
+    dest = np.searchsorted(spl, k, side="right")
+    order = np.argsort(dest, kind="stable")
+    assert list(counts) == np.bincount(dest, minlength=parts).tolist()
+    assert np.array_equal(ko.cpu().numpy().view(np.uint32), k[order])
+    assert np.array_equal(vo.cpu().numpy(), v[order])
+
+
 def test_one_shot_c_entry(M):
     from multishiftseg_b200 import _lib as L
     lib = L.load()
