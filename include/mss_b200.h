@@ -170,6 +170,11 @@ MSS_API int mss_sort_pairs(uint32_t *keys, uint8_t *labs, int64_t n, void *works
                    void *stream);
 /* histogram of the top `bits` (<= 16) key bits: hist[1 << bits] int64, overwritten (splitter selection) */
 MSS_API int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int64_t *hist, void *stream);
+/* same over a systematic sample: only every `every`-th group of 4 consecutive keys is counted (every >= 1).
+ * Splitters only have to be IDENTICAL on all ranks and roughly balanced -- exactness never depends on them --
+ * so the multi-GPU evaluator histograms ~2^24 keys per rank instead of all of them. */
+MSS_API int mss_keys_histogram_sampled(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist,
+                               void *stream);
 /* stable partition of (key,label) pairs into `parts` (<= 256) destination ranges:
  * dest(key) = #{ j : key >= splitters[j] }, splitters ascending device array [parts-1].
  * out_counts_host[parts] receives the bucket sizes (synchronises the stream). */
@@ -177,6 +182,21 @@ MSS_API size_t mss_partition_workspace_bytes(int64_t n);
 MSS_API int mss_partition_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n, const uint32_t *splitters,
                         int parts, uint32_t *keys_out, uint8_t *labs_out, int64_t *out_counts_host,
                         void *workspace, size_t workspace_bytes, void *stream);
+/* bucket sizes only (same dest rule as mss_partition_pairs); workspace >= 2048 bytes; synchronises the stream */
+MSS_API int mss_partition_count(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
+                        int64_t *out_counts_host, void *workspace, size_t workspace_bytes, void *stream);
+/* Fused partition + exchange: the same stable partition, but bucket d is stored straight into ITS OWN pair of
+ * buffers -- typically the receive buffers of GPU d, mapped into this process (peer / symmetric memory), so the
+ * stores travel over NVLink and no NCCL all-to-all and no local staging copy is needed.
+ *   dst_keys_host[d], dst_labs_host[d]  device addresses (as integers) of bucket d's uint32 / uint8 buffers
+ *   dst_offsets_host[d]                 element offset inside them where this rank's block starts
+ * The caller sizes the blocks with mss_partition_count (+ an all-gather across ranks) and must order this call
+ * against the peers' use of the buffers (barrier before and after).  workspace: mss_partition_workspace_bytes(n).
+ * Synchronises the stream. */
+MSS_API int mss_partition_scatter_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n,
+                                const uint32_t *splitters, int parts, const uint64_t *dst_keys_host,
+                                const uint64_t *dst_labs_host, const int64_t *dst_offsets_host,
+                                void *workspace, size_t workspace_bytes, void *stream);
 /* sorted pairs -> per distinct key cumulative counts: tps[k] = pos_before + #pos at positions <= end_k,
  * fps[k] = idx_before + end_k + 1 - tps[k] (int64).  tps/fps need room for n entries.  *T_host = number
  * of distinct keys, pn_host = {#pos, #neg} of this slice (synchronises the stream). */

@@ -64,8 +64,11 @@ SIGNATURES = {
     "mss_sort_pairs_workspace_bytes": (_sz, [_i64]),
     "mss_sort_pairs": (_i, [_p, _p, _i64, _p, _sz, _p]),
     "mss_keys_histogram": (_i, [_p, _i64, _i, _p, _p]),
+    "mss_keys_histogram_sampled": (_i, [_p, _i64, _i, _i, _p, _p]),
     "mss_partition_workspace_bytes": (_sz, [_i64]),
     "mss_partition_pairs": (_i, [_p, _p, _i64, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "mss_partition_count": (_i, [_p, _i64, _p, _i, _p, _p, _sz, _p]),
+    "mss_partition_scatter_pairs": (_i, [_p, _p, _i64, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "mss_counts_workspace_bytes": (_sz, [_i64]),
     "mss_counts_from_sorted": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "mss_tail_workspace_bytes": (_sz, [_i64]),

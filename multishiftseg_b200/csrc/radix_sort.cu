@@ -254,14 +254,20 @@ struct SweepSmem {
     unsigned scan[SORT_WARPS];
     unsigned tile;
 };
+// MULTI-destination scatter (multi-GPU exchange): bucket d goes to its own pair of buffers, which may live in
+// a PEER GPU's memory (NVLink stores); dst[d] / dst[RADIX + d] = base addresses of bucket d's key / label buffer
+struct MultiDst {
+    const unsigned long long *table;         // device array [2 * RADIX], or null: single destination (keys_out, vals_out)
+};
 
 // FULL: the tile holds exactly SORT_TILE pairs (every tile but possibly the last): no bounds predicates.
-template <typename DigitFn, bool FULL>
+template <typename DigitFn, bool FULL, bool MULTI>
 __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__restrict__ keys_in,
                                            uint32_t *__restrict__ keys_out, const uint8_t *__restrict__ vals_in,
                                            uint8_t *__restrict__ vals_out, long long n,
                                            const unsigned long long *__restrict__ bin_base,
-                                           unsigned long long *tile_status, DigitFn digit_of, unsigned tile) {
+                                           unsigned long long *tile_status, DigitFn digit_of, unsigned tile,
+                                           MultiDst multi) {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long tile_base = (long long)tile * SORT_TILE;
     const int tile_n = FULL ? SORT_TILE : (int)(n - tile_base);
@@ -388,19 +394,25 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
         const int p = i * SORT_THREADS + tid;
         if (FULL || p < tile_n) {
             const uint32_t k = sm.keys[p];
-            const unsigned long long o = sm.global[digit_of(k)] + p;
-            keys_out[o] = k;
-            vals_out[o] = sm.vals[p];
+            const unsigned d = digit_of(k);
+            const unsigned long long o = sm.global[d] + p;
+            if (MULTI) {
+                reinterpret_cast<uint32_t *>(__ldg(multi.table + d))[o] = k;
+                reinterpret_cast<uint8_t *>(__ldg(multi.table + RADIX + d))[o] = sm.vals[p];
+            } else {
+                keys_out[o] = k;
+                vals_out[o] = sm.vals[p];
+            }
         }
     }
 }
 
-template <typename DigitFn>
+template <typename DigitFn, bool MULTI = false>
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out,
                      const uint8_t *__restrict__ vals_in, uint8_t *__restrict__ vals_out, long long n,
                      const unsigned long long *__restrict__ bin_base, unsigned long long *tile_status,
-                     unsigned *tile_counter, DigitFn digit_of) {
+                     unsigned *tile_counter, DigitFn digit_of, MultiDst multi = MultiDst{nullptr}) {
     __shared__ SweepSmem sm;
     const unsigned tid = threadIdx.x;
     if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);   // tiles are numbered in start order: the
@@ -409,9 +421,9 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict_
     __syncthreads();
     const unsigned tile = sm.tile;
     if ((long long)(tile + 1) * SORT_TILE <= n)
-        sweep_tile<DigitFn, true>(sm, keys_in, keys_out, vals_in, vals_out, n, bin_base, tile_status, digit_of, tile);
+        sweep_tile<DigitFn, true, MULTI>(sm, keys_in, keys_out, vals_in, vals_out, n, bin_base, tile_status, digit_of, tile, multi);
     else
-        sweep_tile<DigitFn, false>(sm, keys_in, keys_out, vals_in, vals_out, n, bin_base, tile_status, digit_of, tile);
+        sweep_tile<DigitFn, false, MULTI>(sm, keys_in, keys_out, vals_in, vals_out, n, bin_base, tile_status, digit_of, tile, multi);
 }
 
 // top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536).
@@ -440,27 +452,35 @@ __device__ __forceinline__ void kh_add(unsigned *s_hist, unsigned b, bool valid)
 }
 
 __global__ void __launch_bounds__(KH_THREADS, 1)
-keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift, unsigned nbins,
+keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift, unsigned nbins, int every,
                       unsigned long long *__restrict__ hist) {
     extern __shared__ __align__(16) unsigned s_hist[];
+    __shared__ unsigned s_outside;      // keys of this CTA's chunk that fell outside the current window
     // contiguous chunk of whole uint4 groups per CTA; the <= 3 + 3 unaligned head / tail keys go to CTA 0
     const long long head = min(n, (long long)(((16 - ((uintptr_t)keys & 15)) & 15) >> 2));
-    const long long groups4 = (n - head) >> 2;
+    const long long groups_all = (n - head) >> 2;
+    // every > 1: systematic sample -- only uint4 group number j * every (j = 0, 1, ...) is counted
+    const long long groups4 = (groups_all + every - 1) / every;
     const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + head);
     const long long per = (groups4 + gridDim.x - 1) / gridDim.x;
     const long long g0 = min(groups4, (long long)blockIdx.x * per), g1 = min(groups4, g0 + per);
     const long long iters = (g1 - g0 + KH_THREADS - 1) / KH_THREADS;          // uniform per CTA (ballots inside)
-    for (unsigned base = 0; base < nbins; base += KH_WINDOW) {
+    bool more = true;                                                          // CTA-uniform
+    for (unsigned base = 0; base < nbins && more; base += KH_WINDOW) {
         for (int i = threadIdx.x; i < KH_WINDOW; i += KH_THREADS) s_hist[i] = 0;
+        if (threadIdx.x == 0) s_outside = 0;
         __syncthreads();
+        unsigned outside = 0;
         for (long long it = 0; it < iters; it++) {
             const long long g = g0 + it * KH_THREADS + threadIdx.x;
             const bool in = g < g1;
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (in) v = __ldg(k4 + g);
+            if (in) v = __ldg(k4 + g * every);
             const unsigned b0 = (v.x >> shift) - base, b1 = (v.y >> shift) - base, b2 = (v.z >> shift) - base,
                            b3 = (v.w >> shift) - base;
             // the lane's own four keys first: adjacent pixels usually share a bin
+            if (in) outside += (b0 >= (unsigned)KH_WINDOW) + (b1 >= (unsigned)KH_WINDOW) + (b2 >= (unsigned)KH_WINDOW) +
+                               (b3 >= (unsigned)KH_WINDOW);
             const bool same4 = b0 == b1 && b0 == b2 && b0 == b3;
             if (__all_sync(0xffffffffu, same4 || !in)) {
                 // every lane holds four equal bins: one aggregation round with weight 4
@@ -483,14 +503,19 @@ keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift,
                 kh_add(s_hist, b3, in && b3 < (unsigned)KH_WINDOW);
             }
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0)
+        if (blockIdx.x == 0 && threadIdx.x == 0 && every == 1)
             for (long long i = 0; i < n; i++) {
-                if (i == head) i += groups4 << 2;
+                if (i == head) i += groups_all << 2;
                 if (i >= n) break;
                 const unsigned b = (__ldg(keys + i) >> shift) - base;
                 if (b < (unsigned)KH_WINDOW) atomicAdd(s_hist + b, 1u);
+                else outside++;
             }
+        if (outside) atomicAdd(&s_outside, 1u);
         __syncthreads();
+        // windows are visited in ascending order and the unsigned compare also counts the bins BELOW the window
+        // as outside, so "nothing outside" means every key of the chunk has been counted: skip the rest
+        more = s_outside != 0;
         for (int i = threadIdx.x; i < KH_WINDOW && base + i < nbins; i += KH_THREADS)
             if (s_hist[i]) atomicAdd(hist + base + i, (unsigned long long)s_hist[i]);
         __syncthreads();
@@ -581,7 +606,19 @@ extern "C" int mss_sort_pairs(uint32_t *keys, uint8_t *labs, int64_t n, void *wo
     return MSS_OK;   // 4 passes: the result is back in (keys, labs)
 }
 
+static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist, void *stream);
+
 extern "C" int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int64_t *hist, void *stream) {
+    return keys_histogram(keys, n, bits, 1, hist, stream);
+}
+
+extern "C" int mss_keys_histogram_sampled(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist,
+                                          void *stream) {
+    MSS_REQUIRE(every >= 1, "mss_keys_histogram_sampled: every must be >= 1");
+    return keys_histogram(keys, n, bits, every, hist, stream);
+}
+
+static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist, void *stream) {
     MSS_REQUIRE(bits >= 1 && bits <= 16 && hist, "mss_keys_histogram: bits must be 1..16");
     MSS_REQUIRE(n >= 0, "mss_keys_histogram: n < 0");
     cudaStream_t st = (cudaStream_t)stream;
@@ -594,15 +631,15 @@ extern "C" int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int
         kh_attr.store(true);
     }
     // one CTA per SM (128 KB window each); small inputs use fewer CTAs (>= 16 K keys per CTA)
-    int grid = (int)std::max<long long>(1, std::min<long long>((n + 16383) / 16384, (long long)sm_count()));
-    keys_histogram_kernel<<<grid, KH_THREADS, KH_SMEM, st>>>(keys, n, 32 - bits, 1u << bits, (unsigned long long *)hist);
+    int grid = (int)std::max<long long>(1, std::min<long long>((n / every + 16383) / 16384, (long long)sm_count()));
+    keys_histogram_kernel<<<grid, KH_THREADS, KH_SMEM, st>>>(keys, n, 32 - bits, 1u << bits, every, (unsigned long long *)hist);
     MSS_CHECK_LAUNCH();
     return MSS_OK;
 }
 
 extern "C" size_t mss_partition_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
-    return RADIX * 8 + 256 + 256 + 2 * sort_tiles(n) * RADIX * 8 + 4096;
+    return 3 * RADIX * 8 + 256 + 256 + 2 * sort_tiles(n) * RADIX * 8 + 4096;
 }
 
 // exclusive prefix of the bucket sizes
@@ -641,14 +678,33 @@ partition_count_small_kernel(const uint32_t *__restrict__ keys, long long n, Spl
     for (int p = 0; p < PC_SMALL; p++) s_c[p * 256 + threadIdx.x] = 0;
     if (threadIdx.x < PC_SMALL) s_spl[threadIdx.x] = ((int)threadIdx.x < dg.nspl) ? dg.spl[threadIdx.x] : 0xFFFFFFFFu;
     __syncthreads();
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t k = __ldg(keys + i);
+    const int nspl = dg.nspl;
+    auto tally = [&](uint32_t k) {
         unsigned d = 0;
 #pragma unroll
-        for (int j = 0; j < PC_SMALL - 1; j++) d += (j < dg.nspl && k >= s_spl[j]);   // dest = #{j : key >= spl[j]}
+        for (int j = 0; j < PC_SMALL - 1; j++) d += (j < nspl && k >= s_spl[j]);   // dest = #{j : key >= spl[j]}
         s_c[d * 256 + threadIdx.x]++;
+    };
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long head = min(n, (long long)(((16 - ((uintptr_t)keys & 15)) & 15) >> 2));
+    const long long groups4 = (n - head) >> 2;
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + head);
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; g + stride < groups4; g += 2 * stride) {                    // two 16-byte loads in flight per thread
+        const uint4 a = __ldg(k4 + g), b = __ldg(k4 + g + stride);
+        tally(a.x); tally(a.y); tally(a.z); tally(a.w);
+        tally(b.x); tally(b.y); tally(b.z); tally(b.w);
     }
+    if (g < groups4) {
+        const uint4 a = __ldg(k4 + g);
+        tally(a.x); tally(a.y); tally(a.z); tally(a.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = 0; i < n; i++) {
+            if (i == head) i += groups4 << 2;
+            if (i >= n) break;
+            tally(__ldg(keys + i));
+        }
     __syncthreads();
     // warp w sums destinations w, w + 8
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -659,6 +715,71 @@ partition_count_small_kernel(const uint32_t *__restrict__ keys, long long n, Spl
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0 && acc) atomicAdd(counts + p, acc);
     }
+}
+
+static void launch_partition_count(const uint32_t *keys, int64_t n, SplitterDigit dg, int parts,
+                                   unsigned long long *counts, cudaStream_t st) {
+    int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
+    if (parts <= PC_SMALL) partition_count_small_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
+    else partition_count_tiles_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
+}
+
+extern "C" int mss_partition_count(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
+                                   int64_t *out_counts_host, void *workspace, size_t workspace_bytes, void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= RADIX, "mss_partition_count: parts must be 1..256");
+    MSS_REQUIRE(n >= 0 && out_counts_host, "mss_partition_count: bad arguments");
+    for (int j = 0; j < parts; j++) out_counts_host[j] = 0;
+    if (n == 0) return MSS_OK;
+    MSS_REQUIRE(keys && workspace && workspace_bytes >= RADIX * 8 && (parts == 1 || splitters), "mss_partition_count: null pointer / workspace < 2048 bytes");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *counts = (unsigned long long *)workspace;
+    MSS_CHECK_CUDA(cudaMemsetAsync(counts, 0, RADIX * 8, st));
+    launch_partition_count(keys, n, SplitterDigit{splitters, parts - 1}, parts, counts, st);
+    MSS_CHECK_LAUNCH();
+    unsigned long long h[RADIX];
+    MSS_CHECK_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, st));
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < parts; j++) out_counts_host[j] = (int64_t)h[j];
+    return MSS_OK;
+}
+
+extern "C" int mss_partition_scatter_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n,
+                                           const uint32_t *splitters, int parts, const uint64_t *dst_keys_host,
+                                           const uint64_t *dst_labs_host, const int64_t *dst_offsets_host,
+                                           void *workspace, size_t workspace_bytes, void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= RADIX, "mss_partition_scatter_pairs: parts must be 1..256");
+    MSS_REQUIRE(n >= 0 && dst_keys_host && dst_labs_host && dst_offsets_host, "mss_partition_scatter_pairs: bad arguments");
+    if (n == 0) return MSS_OK;
+    MSS_REQUIRE(keys && labs && workspace && (parts == 1 || splitters), "mss_partition_scatter_pairs: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tiles = sort_tiles(n);
+    Carver c(workspace, workspace_bytes);
+    unsigned long long *base = c.take<unsigned long long>(RADIX);          // element offset of this rank's block in bucket d
+    unsigned long long *table = c.take<unsigned long long>(2 * RADIX);     // destination base addresses
+    unsigned *counter = c.take<unsigned>(64);
+    unsigned long long *status = c.take<unsigned long long>(tiles * RADIX);
+    if (!c.ok()) {
+        set_error("mss_partition_scatter_pairs: workspace too small (%zu < %zu)", workspace_bytes, mss_partition_workspace_bytes(n));
+        return MSS_ERR_WORKSPACE;
+    }
+    unsigned long long h[3 * RADIX];
+    for (int j = 0; j < RADIX; j++) {
+        h[j] = (j < parts) ? (unsigned long long)dst_offsets_host[j] : 0ull;
+        h[RADIX + j] = (j < parts) ? (unsigned long long)dst_keys_host[j] : 0ull;
+        h[2 * RADIX + j] = (j < parts) ? (unsigned long long)dst_labs_host[j] : 0ull;
+        if (j < parts) MSS_REQUIRE(dst_keys_host[j] && dst_labs_host[j] && dst_offsets_host[j] >= 0, "mss_partition_scatter_pairs: bad destination %d", j);
+    }
+    MSS_CHECK_CUDA(cudaMemsetAsync(counter, 0, (size_t)((char *)(status + tiles * RADIX) - (char *)counter), st));
+    // base and table are adjacent in the carve (both 256-byte aligned, RADIX * 8 = 2048 bytes): one copy
+    MSS_REQUIRE((char *)table == (char *)base + RADIX * 8, "mss_partition_scatter_pairs: internal layout");
+    MSS_CHECK_CUDA(cudaMemcpyAsync(base, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    SplitterDigit dg{splitters, parts - 1};
+    onesweep_pass_kernel<SplitterDigit, true><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
+        keys, nullptr, labs, nullptr, n, base, status, counter, dg, MultiDst{table});
+    MSS_CHECK_LAUNCH();
+    // the host staging array must outlive the async copy
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    return MSS_OK;
 }
 
 extern "C" int mss_partition_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n, const uint32_t *splitters,
@@ -683,9 +804,7 @@ extern "C" int mss_partition_pairs(const uint32_t *keys, const uint8_t *labs, in
     }
     MSS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)((char *)(status + tiles * RADIX) - (char *)workspace), st));
     SplitterDigit dg{splitters, parts - 1};
-    int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
-    if (parts <= PC_SMALL) partition_count_small_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
-    else partition_count_tiles_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
+    launch_partition_count(keys, n, dg, parts, counts, st);
     MSS_CHECK_LAUNCH();
     partition_bases_kernel<<<1, RADIX, 0, st>>>(counts, base);
     MSS_CHECK_LAUNCH();

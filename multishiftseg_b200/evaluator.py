@@ -32,6 +32,13 @@ import torch
 from . import _lib as L
 
 HIST_BITS = 16
+SAMPLE_LOG2 = 24          # target number of sampled keys per rank for the splitter histogram
+
+
+# peer-mapped receive buffers are expensive to set up (allocation + handle exchange): one per (device, group),
+# grown collectively when a dataset needs more (the needed capacity is computed from all-gathered counts, so
+# every rank takes the same decision)
+_PEER_CACHE: dict = {}
 
 
 class CudaBackend:
@@ -59,11 +66,12 @@ class CudaBackend:
         return buf.keys[:m], buf.labs[:m]
 
     # -- integer stages
-    def histogram(self, keys: torch.Tensor, m: int, bits: int) -> torch.Tensor:
+    def histogram(self, keys: torch.Tensor, m: int, bits: int, every: int = 1) -> torch.Tensor:
+        """Histogram of the top ``bits`` key bits over every ``every``-th group of 4 keys (1 = all keys)."""
         hist = torch.empty(1 << bits, dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
-            L.check(L.load().mss_keys_histogram(keys.data_ptr(), m, bits, hist.data_ptr(), L.stream_ptr(self.device)),
-                    "mss_keys_histogram")
+            L.check(L.load().mss_keys_histogram_sampled(keys.data_ptr(), m, bits, int(every), hist.data_ptr(),
+                                                        L.stream_ptr(self.device)), "mss_keys_histogram_sampled")
         return hist
 
     def partition(self, keys, labs, m: int, splitters: Sequence[int], parts: int):
@@ -80,6 +88,60 @@ class CudaBackend:
                                             keys_out.data_ptr(), labs_out.data_ptr(), counts, ws.data_ptr(), nbytes,
                                             L.stream_ptr(self.device)), "mss_partition_pairs")
         return keys_out[:m], labs_out[:m], [int(c) for c in counts]
+
+    def partition_count(self, keys, m: int, splitters: Sequence[int], parts: int) -> List[int]:
+        import ctypes as C
+        lib = L.load()
+        spl = torch.from_numpy(np.asarray(list(splitters) + [0], dtype=np.uint32).view(np.int32)).to(self.device)
+        counts = (C.c_int64 * parts)()
+        ws = L.workspace(4096, self.device)
+        with torch.cuda.device(self.device):
+            L.check(lib.mss_partition_count(keys.data_ptr(), m, spl.data_ptr(), parts, counts, ws.data_ptr(), 4096,
+                                            L.stream_ptr(self.device)), "mss_partition_count")
+        return [int(c) for c in counts]
+
+    def partition_scatter(self, keys, labs, m: int, splitters: Sequence[int], parts: int, dst_keys: Sequence[int],
+                          dst_labs: Sequence[int], dst_offsets: Sequence[int]):
+        """Fused partition + exchange: bucket d is stored at element offset ``dst_offsets[d]`` of the buffers at
+        device addresses ``dst_keys[d]`` / ``dst_labs[d]`` (peer memory for d != this rank)."""
+        import ctypes as C
+        lib = L.load()
+        spl = torch.from_numpy(np.asarray(list(splitters) + [0], dtype=np.uint32).view(np.int32)).to(self.device)
+        dk = (C.c_uint64 * parts)(*[int(x) for x in dst_keys])
+        dl = (C.c_uint64 * parts)(*[int(x) for x in dst_labs])
+        do = (C.c_int64 * parts)(*[int(x) for x in dst_offsets])
+        nbytes = lib.mss_partition_workspace_bytes(m)
+        ws = L.workspace(nbytes, self.device)
+        with torch.cuda.device(self.device):
+            L.check(lib.mss_partition_scatter_pairs(keys.data_ptr(), labs.data_ptr(), m, spl.data_ptr(), parts, dk, dl, do,
+                                                    ws.data_ptr(), nbytes, L.stream_ptr(self.device)),
+                    "mss_partition_scatter_pairs")
+
+    # -- peer-mapped receive buffers (torch symmetric memory: every rank can store into every rank's buffer)
+    def peer_buffers(self, capacity: int, group):
+        """-> (keys int32 [capacity], labs uint8 [capacity], key_ptrs[world], lab_ptrs[world], handle) or raises."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        cap = int(capacity)
+        ck = (str(self.device), id(group))
+        cached = _PEER_CACHE.get(ck)
+        if cached is not None and cached["cap"] >= cap:
+            return cached
+        grp = group if group is not None else dist.group.WORLD
+        if getattr(torch, "__version__", "2.11") < "2.8":       # older torch: the group must be enabled first
+            try:
+                symm.enable_symm_mem_for_group(grp.group_name)
+            except Exception:
+                pass
+        kb = (cap * 4 + 255) // 256 * 256
+        raw = symm.empty(kb + cap, dtype=torch.uint8, device=self.device)     # one allocation: [keys | labs]
+        hdl = symm.rendezvous(raw, grp)
+        keys = raw[: cap * 4].view(torch.int32)
+        labs = raw[kb: kb + cap]
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        _PEER_CACHE[ck] = {"cap": cap, "raw": raw, "hdl": hdl, "keys": keys, "labs": labs,
+                           "key_ptrs": ptrs, "lab_ptrs": [p + kb for p in ptrs]}
+        return _PEER_CACHE[ck]
 
     def sort(self, keys, labs, m: int):
         from .metric import sort_pairs
@@ -127,7 +189,11 @@ class StreamingEvaluator:
     torch.distributed is initialised; single-process otherwise)."""
 
     def __init__(self, capacity: int, device=None, train_id_in: int = 0, train_id_out: int = 1, backend=None,
-                 distributed: Optional[bool] = None, group=None):
+                 distributed: Optional[bool] = None, group=None, exchange: str = "auto"):
+        """``exchange``: "p2p" = fused partition + peer-memory stores over NVLink, "nccl" = local partition +
+        all-to-all, "auto" = p2p when the backend offers peer buffers (falls back to nccl if mapping fails)."""
+        assert exchange in ("auto", "p2p", "nccl")
+        self.exchange = exchange
         self.backend = backend if backend is not None else CudaBackend(device)
         self.id_in, self.id_out = int(train_id_in), int(train_id_out)
         self.buf = self.backend.new_buffer(int(capacity))
@@ -190,24 +256,61 @@ class StreamingEvaluator:
 
         # 2. global histogram of the top key bits -> splitters
         keys, labs = be.pairs(self.buf, m)
-        hist = be.histogram(keys, m, HIST_BITS)
+        # a systematic sample of ~2^24 keys per rank is plenty to balance the ranges; any splitters give the exact
+        # result as long as every rank uses the same ones, which the all_reduce guarantees
+        every = max(1, M // (world << SAMPLE_LOG2))
+        hist = be.histogram(keys, m, HIST_BITS, every)
         dist.all_reduce(hist, group=g)
         splitters = choose_splitters(hist.cpu().numpy(), world)
         mark("histogram_splitters")
 
-        # 3. local partition by destination rank, exchange
-        pk, pl, send_counts = be.partition(keys, labs, m, splitters, world)
-        mark("partition")
-        cm = be.tensor(send_counts, torch.int64)
-        all_counts = be.empty(world * world, torch.int64)
-        dist.all_gather_into_tensor(all_counts, cm, group=g)
-        all_counts = all_counts.view(world, world).cpu().numpy()      # [src, dst]
-        recv_counts = [int(c) for c in all_counts[:, rank]]
-        m2 = int(sum(recv_counts))
-        rk, rl = be.empty(max(m2, 1), torch.int32), be.empty(max(m2, 1), torch.uint8)
-        dist.all_to_all_single(rk[:m2], pk, recv_counts, send_counts, group=g)
-        dist.all_to_all_single(rl[:m2], pl, recv_counts, send_counts, group=g)
-        mark("all_to_all")
+        # 3. exchange by key range
+        exchange = self.exchange
+        if exchange == "auto":
+            exchange = "p2p" if hasattr(be, "peer_buffers") and not getattr(self, "_p2p_failed", False) else "nccl"
+        if exchange == "p2p":
+            # 3a. fused: count -> all-gather of the counts -> ONE kernel that partitions and stores every bucket
+            #     straight into its owner's receive buffer over NVLink (no staging copy, no all-to-all)
+            send_counts = be.partition_count(keys, m, splitters, world)
+            cm = be.tensor(send_counts, torch.int64)
+            all_counts = be.empty(world * world, torch.int64)
+            dist.all_gather_into_tensor(all_counts, cm, group=g)
+            all_counts = all_counts.view(world, world).cpu().numpy()      # [src, dst]
+            recv_counts = [int(c) for c in all_counts[:, rank]]
+            m2 = int(sum(recv_counts))
+            need = int(all_counts.sum(axis=0).max())                      # identical on every rank
+            try:
+                pb = be.peer_buffers(max(need + need // 8, 1 << 20), g)   # collective (re)allocation when it grows
+            except Exception as e:                                        # no peer access on this box: NCCL path
+                self._p2p_failed, self.p2p_error = True, repr(e)
+                pb = None
+            ok = be.tensor([0 if pb is None else 1], torch.int64)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=g)
+            if int(ok.item()) == 1:
+                mark("count")
+                offsets = [int(all_counts[:rank, d].sum()) for d in range(world)]   # my block inside rank d's buffer
+                dist.barrier(group=g)                                     # peers are done with the previous contents
+                be.partition_scatter(keys, labs, m, splitters, world, pb["key_ptrs"], pb["lab_ptrs"], offsets)
+                dist.barrier(group=g)                                     # every rank's stores have landed
+                rk, rl = pb["keys"], pb["labs"]
+                mark("partition_scatter_p2p")
+            else:
+                self._p2p_failed = True
+                exchange = "nccl"
+        if exchange == "nccl":
+            # 3b. local partition by destination rank + NCCL all-to-all
+            pk, pl, send_counts = be.partition(keys, labs, m, splitters, world)
+            mark("partition")
+            cm = be.tensor(send_counts, torch.int64)
+            all_counts = be.empty(world * world, torch.int64)
+            dist.all_gather_into_tensor(all_counts, cm, group=g)
+            all_counts = all_counts.view(world, world).cpu().numpy()      # [src, dst]
+            recv_counts = [int(c) for c in all_counts[:, rank]]
+            m2 = int(sum(recv_counts))
+            rk, rl = be.empty(max(m2, 1), torch.int32), be.empty(max(m2, 1), torch.uint8)
+            dist.all_to_all_single(rk[:m2], pk, recv_counts, send_counts, group=g)
+            dist.all_to_all_single(rl[:m2], pl, recv_counts, send_counts, group=g)
+            mark("all_to_all")
 
         # 4. local sort + run-length counts with global prefixes
         be.sort(rk, rl, m2)
@@ -244,7 +347,8 @@ class StreamingEvaluator:
         res = be.tail(tps_all, fps_all, recall_level)
         mark("tail")
         self.last_exchange = {"send_counts": send_counts, "recv_counts": recv_counts, "splitters": splitters,
-                              "thresholds_per_rank": Ts,
+                              "thresholds_per_rank": Ts, "exchange": exchange,
+                              "p2p_error": getattr(self, "p2p_error", None),
                               "phase_ms": {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}}
         return res
 

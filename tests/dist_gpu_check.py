@@ -28,19 +28,21 @@ def main():
         s, l = gi.metric_case(500 + ci, n, mode, p_ood, p_ign, label_dtype="uint8")
         img = max(n // 16, 1)
         chunks = [(i, min(i + img, n)) for i in range(0, n, img)]
-        ev = StreamingEvaluator(n // world + 2 * img, distributed=True)
-        for a, b in chunks[rank::world]:
-            ev.update(torch.from_numpy(s[a:b]).cuda(), torch.from_numpy(l[a:b]).cuda())
-        got = ev.compute()
-        got = None if got is None else tuple(float(v) for v in got)
         want = c_oracle.eval_ood_measure(s, l)
         one = metric.eval_ood_measure(s, l)
         one = None if one is None else tuple(float(v) for v in one)
-        good = (got == want == one)
-        ok &= good
-        if rank == 0:
-            print(f"[world {world}] {mode:6s} n={n:8d} multi-gpu == 1-gpu == oracle: {good}  {got}  exch={ev.last_exchange['recv_counts'] if good and got else ''}",
-                  flush=True)
+        for exch in ("p2p", "nccl"):          # fused peer-memory scatter, and partition + NCCL all-to-all
+            ev = StreamingEvaluator(n // world + 2 * img, distributed=True, exchange=exch)
+            for a, b in chunks[rank::world]:
+                ev.update(torch.from_numpy(s[a:b]).cuda(), torch.from_numpy(l[a:b]).cuda())
+            got = ev.compute()
+            got = None if got is None else tuple(float(v) for v in got)
+            good = (got == want == one)
+            ok &= good
+            if rank == 0:
+                x = ev.last_exchange if good and got else {}
+                print(f"[world {world}] {mode:6s} n={n:8d} {exch:4s}->{x.get('exchange')} multi-gpu == 1-gpu == oracle: {good}  {got}  "
+                      f"recv={x.get('recv_counts', '')} {x.get('p2p_error') or ''}", flush=True)
     # fused DeepLab scoring -> evaluator, sharded images
     g = torch.Generator().manual_seed(7)
     B, H, W = 4, 128, 256

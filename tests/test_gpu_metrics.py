@@ -221,6 +221,21 @@ def test_keys_histogram_skewed_and_unaligned(M, bits):
         assert np.array_equal(hist.cpu().numpy(), np.bincount(k[1:] >> (32 - bits), minlength=1 << bits))
 
 
+def test_keys_histogram_sampled(M):
+    from multishiftseg_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(9)
+    n = 1_000_003
+    k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    kt = torch.from_numpy(k.view(np.int32)).cuda()                          # 16-byte aligned: groups start at key 0
+    st = torch.cuda.current_stream().cuda_stream
+    for every in [1, 2, 7, 64]:
+        hist = torch.empty(1 << 16, dtype=torch.int64, device="cuda")
+        assert lib.mss_keys_histogram_sampled(kt.data_ptr(), n, 16, every, hist.data_ptr(), st) == 0
+        sample = k if every == 1 else k[: n - n % 4].reshape(-1, 4)[::every].reshape(-1)
+        assert np.array_equal(hist.cpu().numpy(), np.bincount(sample >> 16, minlength=1 << 16))
+
+
 @pytest.mark.parametrize("parts", [1, 2, 8, 16, 17, 200])
 def test_partition_many_and_few_parts(M, parts):
     from multishiftseg_b200 import _lib as L
@@ -245,6 +260,33 @@ def test_partition_many_and_few_parts(M, parts):
     assert list(counts) == np.bincount(dest, minlength=parts).tolist()
     assert np.array_equal(ko.cpu().numpy().view(np.uint32), k[order])
     assert np.array_equal(vo.cpu().numpy(), v[order])
+
+
+@pytest.mark.parametrize("parts", [2, 8])
+def test_partition_scatter_to_separate_buffers(M, parts):
+    """mss_partition_count + mss_partition_scatter_pairs with one buffer pair per bucket (on a multi-GPU box these
+    are the peers' receive buffers; here they are local): == the stable partition, bucket by bucket."""
+    from multishiftseg_b200.evaluator import CudaBackend
+    be = CudaBackend("cuda")
+    rng = np.random.default_rng(parts)
+    n = 1_000_001
+    k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    v = rng.integers(0, 2, size=n, dtype=np.uint8)
+    spl = [int(x) for x in np.sort(rng.choice(k, size=parts - 1, replace=False))]
+    kt, vt = torch.from_numpy(k.view(np.int32)).cuda(), torch.from_numpy(v).cuda()
+    counts = be.partition_count(kt, n, spl, parts)
+    dest = np.searchsorted(np.asarray(spl, dtype=np.uint32), k, side="right")
+    assert counts == np.bincount(dest, minlength=parts).tolist()
+    off = 5                                                           # this "rank's" block starts at element 5
+    bk = [torch.full((c + off + 3,), -1, dtype=torch.int32, device="cuda") for c in counts]
+    bl = [torch.full((c + off + 3,), 9, dtype=torch.uint8, device="cuda") for c in counts]
+    be.partition_scatter(kt, vt, n, spl, parts, [t.data_ptr() for t in bk], [t.data_ptr() for t in bl], [off] * parts)
+    for d in range(parts):
+        sel = dest == d
+        assert np.array_equal(bk[d].cpu().numpy().view(np.uint32)[off:off + counts[d]], k[sel])      # stable
+        assert np.array_equal(bl[d].cpu().numpy()[off:off + counts[d]], v[sel])
+        assert (bk[d][:off] == -1).all() and (bk[d][off + counts[d]:] == -1).all()                    # nothing outside the block
+        assert (bl[d][:off] == 9).all() and (bl[d][off + counts[d]:] == 9).all()
 
 
 def test_one_shot_c_entry(M):
