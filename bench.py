@@ -266,7 +266,36 @@ def extra_m2f(batch=8):
                      "contraction_TFLOPs": flop / ms / 1e9}
     out["workload"] = f"cfg3: M2F semantic_inference Q=100 C=19+1 256x512->1024x2048 batch {batch}"
     out["fma_roofline_TFLOPs"] = 148 * 128 * 2 * 1.965e9 / 1e12
+    # binding pipe of the tcgen05 kernel: the two MUFU ops (ex2 + rcp) of each of the Q sigmoids per pixel,
+    # 16 lanes/clk/SM -> 2 * Q * px / (16 * 148 * f_SM)
+    floor_ms = 2 * 100 * batch * H * W / (16 * 148 * 1.965e9) * 1e3
+    out["mufu_floor_ms"] = floor_ms
+    out["frac_of_mufu_roofline"] = floor_ms / out["anomaly_score"]["ms"]
     return out
+
+
+def extra_confusion():
+    """mIoU confusion histogram fused with argmax over the cfg-2 logit batch (76 + 1 B/px read)."""
+    from multishiftseg_b200 import segmetric
+    g = torch.Generator(device="cuda").manual_seed(5000)
+    x = torch.randn((B_PER_GPU, C, H, W), device="cuda", generator=g)
+    gt = torch.randint(0, C, (B_PER_GPU, H, W), device="cuda", generator=g, dtype=torch.int64).to(torch.uint8)
+    acc = segmetric.ConfusionAccumulator(C, "cuda")
+    for _ in range(3):
+        acc.update_from_logits(x, gt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        acc.update_from_logits(x, gt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    px = B_PER_GPU * H * W
+    peak, _, _ = peaks()
+    gbs = px * (4 * C + 1) / ms / 1e6
+    return {"workload": "fused argmax + 19x19 confusion histogram, 16x19x1024x2048 fp32 logits + u8 gt", "ms": ms,
+            "mpix_s": px / ms / 1e3, "algorithmic_GBs": gbs, "frac_of_hbm_peak": gbs / peak}
 
 
 def main():
@@ -362,7 +391,9 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_extra:
         try:
-            line["extra"] = {"metrics": extra_metrics_stage(), "m2f": extra_m2f()}
+            del logits, out
+            torch.cuda.empty_cache()
+            line["extra"] = {"metrics": extra_metrics_stage(), "m2f": extra_m2f(), "confusion": extra_confusion()}
         except Exception as e:   # side measurements must never take the headline down
             line["extra"] = {"error": repr(e)}
     if sampler is not None:

@@ -128,7 +128,7 @@ class CudaBackend:
         if cached is not None and cached["cap"] >= cap:
             return cached
         grp = group if group is not None else dist.group.WORLD
-        if getattr(torch, "__version__", "2.11") < "2.8":       # older torch: the group must be enabled first
+        if tuple(int(x) for x in torch.__version__.split("+")[0].split(".")[:2]) < (2, 8):   # older torch: enable the group first
             try:
                 symm.enable_symm_mem_for_group(grp.group_name)
             except Exception:
@@ -151,6 +151,12 @@ class CudaBackend:
         from .metric import counts_from_sorted
         tps, fps, _, _ = counts_from_sorted(keys, labs, m, pos_before, idx_before)
         return tps, fps
+
+    def counts_local(self, keys, labs, m: int):
+        """-> (tps, fps, #positives) of this slice alone (prefixes of earlier slices not included)."""
+        from .metric import counts_from_sorted
+        tps, fps, n_pos, _ = counts_from_sorted(keys, labs, m, 0, 0)
+        return tps, fps, n_pos
 
     def tail(self, tps, fps, recall_level=0.95):
         from .metric import metrics_tail
@@ -315,17 +321,21 @@ class StreamingEvaluator:
         # 4. local sort + run-length counts with global prefixes
         be.sort(rk, rl, m2)
         mark("sort")
-        lp = int((rl[:m2] != 0).sum().item()) if m2 else 0
+        # local cumulative counts first (they also yield this slice's #positives), global prefixes added afterwards:
+        # tps += positives before this rank, fps += negatives before this rank
+        if m2:
+            tps, fps, lp = be.counts_local(rk, rl, m2)
+        else:
+            tps, fps, lp = be.empty(0, torch.int64), be.empty(0, torch.int64), 0
         mine = be.tensor([m2, lp], torch.int64)
         per_rank = be.empty(2 * world, torch.int64)
         dist.all_gather_into_tensor(per_rank, mine, group=g)
         per_rank = per_rank.view(world, 2).cpu().numpy()
         idx_before = int(per_rank[:rank, 0].sum())
         pos_before = int(per_rank[:rank, 1].sum())
-        if m2:
-            tps, fps = be.counts(rk, rl, m2, pos_before, idx_before)
-        else:
-            tps, fps = be.empty(0, torch.int64), be.empty(0, torch.int64)
+        if tps.numel():
+            tps += pos_before
+            fps += idx_before - pos_before
         mark("counts")
 
         # 5. gather every rank's thresholds (padded to the longest slice), run the identical tail everywhere

@@ -11,6 +11,8 @@ cat $O/bench_$TAG.json; tail -3 $O/bench_$TAG.err
 timeout 300 python bench.py --impl reference --steps 10 --warmup 3 > $O/bench_ref_$TAG.json 2>&1
 cat $O/bench_ref_$TAG.json
 timeout 300 python scratch/bench_sort.py > $O/sort_$TAG.log 2>&1; cat $O/sort_$TAG.log
+timeout 300 python scratch/bench_m2f.py 0 8 4 2 > $O/m2f_$TAG.log 2>&1; cat $O/m2f_$TAG.log
+timeout 600 python bench_sweep.py > $O/sweep_$TAG.json 2> $O/sweep_$TAG.err; cat $O/sweep_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench_$TAG.csv python bench.py --steps 3 --warmup 3 --no-cpu > $O/ncu_bench_$TAG.log 2>&1
 python scratch/ncu_summary.py launches $O/launches_bench_$TAG.csv | head -30
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv python scratch/prof_run2.py all 16 > $O/ncu_list_$TAG.log 2>&1
@@ -21,7 +23,7 @@ cap() {  # name regex part skip
   ncu -i $O/prof_${TAG}_$1.ncu-rep --page source --csv > $O/prof_${TAG}_$1_source.csv 2>/dev/null
 }
 cap score deeplab_score score 1
-cap m2f 'm2f_tc5' m2f 2
+cap m2f 'm2f_tc5q' m2f 2
 cap sweep onesweep_pass eval 5
 cap hist radix_histogram eval 1
 cap runs 'runs_kernel' eval 1
@@ -29,6 +31,8 @@ cap tscan 'tile_scan' eval 1
 cap roc 'roc_compact' eval 1
 cap leaf 'leaf_sum' eval 2
 cap fpr 'fpr_reduce' eval 1
+cap append 'eval_append' eval 1
+python scratch/make_traffic.py $O/prof_${TAG}_score_raw.csv $TAG
 python scratch/ncu_summary.py raw $O/prof_${TAG}_*_raw.csv > $O/ncu_full_${TAG}_summary.txt 2>&1
 while [ $(du -sm $O | cut -f1) -gt 60 ]; do f=$(ls -S $O/*.ncu-rep | head -1); echo "dropping $f"; rm -f $f; done
 du -sh $O

@@ -69,6 +69,10 @@ class NumpyBackend:
         fps = ends + 1 + idx_before - tps
         return torch.from_numpy(tps.astype(np.int64)), torch.from_numpy(fps.astype(np.int64))
 
+    def counts_local(self, keys, labs, m):
+        tps, fps = self.counts(keys, labs, m, 0, 0)
+        return tps, fps, int(labs.numpy()[:m].astype(np.int64).sum())
+
     def tail(self, tps, fps, recall_level=0.95):
         return tuple(np.float64(v) for v in c_oracle.metrics_from_counts(tps.numpy(), fps.numpy(), recall_level))
 
