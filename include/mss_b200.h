@@ -108,6 +108,19 @@ MSS_API int mss_upsample_bilinear(const float *in, int64_t NC, int h, int w, flo
 MSS_API int mss_deeplab_anomaly_score(const float *ood_logits, int64_t B, int C, int h, int w,
                               float *scratch, float *score, int H, int W, void *stream);
 
+/*  DeepLabv3+ head fusion, deepv3.py:279-283: the two bias-free 1x1 convolutions on the decoder
+ * feature map and the energy score in one pass (tcgen05 3xTF32 GEMM, feature read once):
+ *   feature [B, K, hw] NCHW fp32;  w_cls = final[-1].weight, w_ood = ood_head.weight, each [C, K] row-major
+ *   dec1 [B, C, hw] = conv1x1(feature, w_cls)      (deepv3.py:279)   or NULL
+ *   dec2 [B, C, hw] = conv1x1(feature, w_ood)      (deepv3.py:282)   or NULL
+ *   energy [B, hw]  = -logsumexp_c dec2            (deepv3.py:251-253, before the Upsample of :283)   or NULL
+ * Supported: C <= 24, K a multiple of 32 up to 256 (the model: C = 19, K = 256); otherwise
+ * MSS_ERR_UNSUPPORTED.  workspace: mss_deeplab_head_workspace_bytes(K). */
+MSS_API size_t mss_deeplab_head_workspace_bytes(int K);
+MSS_API int mss_deeplab_head(const float *feature, int64_t B, int K, int64_t hw, const float *w_cls,
+                     const float *w_ood, int C, float *dec1, float *dec2, float *energy, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (a4-a7) Mask2Former fused post-head inference.
  *   cls_logits  [B, Q, C+1]        pred_logits / pred_logits_ood

@@ -53,17 +53,6 @@ constexpr size_t tq_smem(bool dup) {
     return (size_t)TQ_PATCH_BYTES + (dup ? 4 : 2) * T5_B_FLOATS * 4 + 128 * 8 + 16 * 8 + 16 + 128;
 }
 
-__device__ __forceinline__ void tc5_st4(uint32_t taddr, const uint32_t (&v)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
-                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
-                 : "memory");
-}
-__device__ __forceinline__ void tc5_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
-}
 __device__ __forceinline__ void stg_stream_f2(float *p, float a, float b) {
     asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }

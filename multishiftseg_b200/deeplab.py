@@ -14,7 +14,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["energy_func", "Upsample", "anomaly_score", "score_maps", "SCORES"]
+__all__ = ["energy_func", "Upsample", "anomaly_score", "score_maps", "head_scores", "SCORES"]
 
 SCORES = ("energy", "maxlogit", "msp", "entropy")
 
@@ -107,6 +107,42 @@ def anomaly_score(ood_logit: torch.Tensor, size: Sequence[int]) -> torch.Tensor:
                                                 H, W, L.stream_ptr(ood_logit.device))
     L.check(rc, "mss_deeplab_anomaly_score")
     return out
+
+
+def head_scores(feature: torch.Tensor, w_cls: torch.Tensor, w_ood: torch.Tensor, size: Optional[Sequence[int]] = None,
+                want_dec2: bool = False):
+    """deepv3.py:279-283 fused: ``feature`` [B, K, h, w] is read ONCE; returns
+
+        dec1 = final[-1](feature)                       [B, C, h, w]   (feed ``Upsample(dec1, x_size[2:])`` for ``logit``)
+        anomaly_score = Upsample(energy_func(ood_head(feature)).unsqueeze(1), size).squeeze(1)   [B, H, W]
+                        (or the head-resolution energy [B, h, w] when ``size`` is None)
+        dec2 (only with ``want_dec2``)
+
+    ``w_cls`` / ``w_ood`` are the weights of the two bias-free 1x1 convolutions ([C, K] or [C, K, 1, 1])."""
+    L.require_cuda(feature, "feature")
+    if feature.dim() != 4:
+        raise ValueError("feature must be [B, K, h, w]")
+    x = feature.float().contiguous()
+    B, K, h, w = x.shape
+    wc = L.require_cuda(w_cls, "w_cls").float().reshape(w_cls.shape[0], -1).contiguous()
+    wo = L.require_cuda(w_ood, "w_ood").float().reshape(w_ood.shape[0], -1).contiguous()
+    Cn = wc.shape[0]
+    if wc.shape != (Cn, K) or wo.shape != (Cn, K):
+        raise ValueError("w_cls and w_ood must both be [C, K] (or [C, K, 1, 1]) with K = feature channels")
+    lib = L.load()
+    dec1 = torch.empty((B, Cn, h, w), dtype=torch.float32, device=x.device)
+    dec2 = torch.empty((B, Cn, h, w), dtype=torch.float32, device=x.device) if want_dec2 else None
+    energy = torch.empty((B, h, w), dtype=torch.float32, device=x.device)
+    nbytes = lib.mss_deeplab_head_workspace_bytes(K)
+    ws = L.workspace(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.mss_deeplab_head(x.data_ptr(), B, K, h * w, wc.data_ptr(), wo.data_ptr(), Cn, dec1.data_ptr(), L.ptr(dec2),
+                                  energy.data_ptr(), ws.data_ptr(), nbytes, L.stream_ptr(x.device))
+    if rc == L.MSS_ERR_UNSUPPORTED:
+        raise L.MssError("deeplab.head_scores: " + L.last_error())
+    L.check(rc, "mss_deeplab_head")
+    score = energy if size is None else Upsample(energy.unsqueeze(1), size).squeeze(1)
+    return (dec1, score, dec2) if want_dec2 else (dec1, score)
 
 
 def score_maps_host(logits_host: torch.Tensor, which: Iterable[str] = ("energy",), scratch: Optional[torch.Tensor] = None,

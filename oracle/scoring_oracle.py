@@ -36,6 +36,19 @@ def deeplab_anomaly_score(ood_logit: torch.Tensor, size) -> torch.Tensor:
     return Upsample(energy_func(ood_logit).unsqueeze(1), size).squeeze(1)
 
 
+def deeplab_head(feature: torch.Tensor, w_cls: torch.Tensor, w_ood: torch.Tensor, size=None):
+    """lib/network/deepv3/deepv3.py:279-283: ``dec1 = self.final[-1](feature)``,
+    ``dec2 = self.ood_head(feature)`` -- both ``nn.Conv2d(256, num_classes, kernel_size=1, bias=False)``
+    (deepv3.py:245-247), i.e. ``F.conv2d`` with a [C, K, 1, 1] weight -- then the energy of dec2 and its
+    align_corners=True upsample.  Returns (dec1, anomaly_score, dec2).  Parity: the ops are torch's own; no
+    reference-generated fixture (the lines sit inside ``forward``, which needs the whole network)."""
+    dec1 = F.conv2d(feature, w_cls.reshape(w_cls.shape[0], -1, 1, 1))
+    dec2 = F.conv2d(feature, w_ood.reshape(w_ood.shape[0], -1, 1, 1))
+    e = energy_func(dec2)
+    score = e if size is None else Upsample(e.unsqueeze(1), size).squeeze(1)
+    return dec1, score, dec2
+
+
 def maxlogit_score(logit: torch.Tensor) -> torch.Tensor:
     """north_star extra score (no reference code): -max_c x."""
     return -logit.max(dim=1)[0]
