@@ -298,6 +298,31 @@ def extra_confusion():
             "mpix_s": px / ms / 1e3, "algorithmic_GBs": gbs, "frac_of_hbm_peak": gbs / peak}
 
 
+def extra_head():
+    """fused DeepLab head (two 1x1 convs + energy), 8 x 256 x 512 x 1024 fp32 features."""
+    from multishiftseg_b200 import deeplab
+    B, K, h, w = 8, 256, 512, 1024
+    g = torch.Generator(device="cuda").manual_seed(6000)
+    feat = torch.relu(torch.randn((B, K, h, w), device="cuda", generator=g))
+    wc = torch.randn((C, K), device="cuda", generator=g) / 16
+    wo = torch.randn((C, K), device="cuda", generator=g) / 16
+    for _ in range(3):
+        deeplab.head_scores(feat, wc, wo)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        deeplab.head_scores(feat, wc, wo)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    px = B * h * w
+    peak, _, _ = peaks()
+    gbs = px * (K * 4 + C * 4 + 4) / ms / 1e6
+    return {"workload": "fused ood_head/final[-1] 1x1 convs + energy, 8x256x512x1024 fp32 features (tcgen05 3xTF32)",
+            "ms": ms, "head_mpix_s": px / ms / 1e3, "algorithmic_GBs": gbs, "frac_of_hbm_peak": gbs / peak}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -393,7 +418,8 @@ def main():
         try:
             del logits, out
             torch.cuda.empty_cache()
-            line["extra"] = {"metrics": extra_metrics_stage(), "m2f": extra_m2f(), "confusion": extra_confusion()}
+            line["extra"] = {"metrics": extra_metrics_stage(), "m2f": extra_m2f(), "confusion": extra_confusion(),
+                             "head": extra_head()}
         except Exception as e:   # side measurements must never take the headline down
             line["extra"] = {"error": repr(e)}
     if sampler is not None:
