@@ -154,6 +154,19 @@ MSS_API int mss_m2f_semantic_inference(const float *cls_logits, const float *mas
                                const int32_t *keep_count, float *extra, int64_t extra_batch_stride,
                                void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
 
+/* (Mask2Former half) the mask-logit contraction in front of the scoring path,
+ * lib/network/mask2former/modeling/transformer_decoder/mask2former_transformer_decoder.py:528-529 (pred_masks)
+ * and :548-549 (pred_masks_ood):   outputs_mask = torch.einsum("bqc,bchw->bqhw", mask_embed, mask_features)
+ *   mask_embed    [B, Q, K]   per-image query embeddings (output of the mask_embed MLP)
+ *   mask_features [B, K, hw]  pixel-decoder features, NCHW fp32, read once
+ *   mask_logits   [B, Q, hw]  = the decoder-resolution masks mss_m2f_semantic_inference takes
+ * tcgen05 3xTF32 GEMM (fp32-level accuracy), one CTA per SM holding the image's pre-split embedding table.
+ * Supported: Q <= 112, K a multiple of 32 up to 256, hw <= 2^31 / 256 (the model: Q = 100, K = 256); otherwise
+ * MSS_ERR_UNSUPPORTED.  workspace: mss_m2f_mask_logits_workspace_bytes(B, K). */
+MSS_API size_t mss_m2f_mask_logits_workspace_bytes(int64_t B, int K);
+MSS_API int mss_m2f_mask_logits(const float *mask_embed, const float *mask_features, int64_t B, int Q, int K,
+                        int64_t hw, float *mask_logits, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (a9-a13) exact, tie-aware AUROC / AP / FPR@95TPR.
  * Replaces eval_ood_measure (lib/utils/metric.py:170-180) and everything below it

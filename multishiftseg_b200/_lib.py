@@ -60,6 +60,8 @@ SIGNATURES = {
     "mss_m2f_workspace_bytes": (_sz, [_i64, _i, _i]),
     "mss_m2f_semantic_inference": (_i, [_p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p,
                                         _p, _i64, _p, _sz, _u, _p]),
+    "mss_m2f_mask_logits_workspace_bytes": (_sz, [_i64, _i]),
+    "mss_m2f_mask_logits": (_i, [_p, _p, _i64, _i, _i, _i64, _p, _p, _sz, _p]),
     "mss_ood_metrics_workspace_bytes": (_sz, [_i64]),
     "mss_ood_metrics": (_i, [_p, _p, _i, _i64, _i64, _i64, _p, _sz, _p, _p, _p]),
     "mss_ood_metrics_from_eval": (_i, [_EV, _p, _sz, _p, _p, _p]),

@@ -16,7 +16,8 @@ import torch.nn.functional as F
 
 from . import _lib as L
 
-__all__ = ["semantic_inference", "get_anomaly_score", "post_head_inference", "anomaly_score_from_lowres"]
+__all__ = ["semantic_inference", "get_anomaly_score", "post_head_inference", "anomaly_score_from_lowres", "mask_logits",
+           "anomaly_score_from_features"]
 
 
 def _keep_queries(mask_cls: torch.Tensor, num_classes: int):
@@ -115,3 +116,38 @@ def anomaly_score_from_lowres(pred_logits_ood: torch.Tensor, pred_masks_ood: tor
     """maskformer_model.py:271-277 + train_m2f.py:387-407 fused: [B, Q, h, w] decoder masks -> [B, H, W] score."""
     _, anomaly, _ = _run(pred_logits_ood, pred_masks_ood, padded_size, size, False, True, False, flags)
     return anomaly
+
+
+def mask_logits(mask_embed: torch.Tensor, mask_features: torch.Tensor) -> torch.Tensor:
+    """mask2former_transformer_decoder.py:529 / :549:
+    ``outputs_mask = torch.einsum("bqc,bchw->bqhw", mask_embed, mask_features)`` -- ``mask_embed`` [B, Q, K],
+    ``mask_features`` [B, K, h, w] -> [B, Q, h, w], on tcgen05 with 3xTF32 (fp32-level accuracy)."""
+    L.require_cuda(mask_embed, "mask_embed")
+    L.require_cuda(mask_features, "mask_features")
+    if mask_embed.dim() != 3 or mask_features.dim() != 4:
+        raise ValueError("mask_embed must be [B, Q, K] and mask_features [B, K, h, w]")
+    e = mask_embed.float().contiguous()
+    f = mask_features.float().contiguous()
+    B, Q, K = e.shape
+    Bf, Kf, h, w = f.shape
+    if (Bf, Kf) != (B, K):
+        raise ValueError(f"mask_embed {tuple(e.shape)} and mask_features {tuple(f.shape)} disagree")
+    lib = L.load()
+    out = torch.empty((B, Q, h, w), dtype=torch.float32, device=f.device)
+    nbytes = lib.mss_m2f_mask_logits_workspace_bytes(B, K)
+    ws = L.workspace(nbytes, f.device)
+    with torch.cuda.device(f.device):
+        rc = lib.mss_m2f_mask_logits(e.data_ptr(), f.data_ptr(), B, Q, K, h * w, out.data_ptr(), ws.data_ptr(), nbytes,
+                                     L.stream_ptr(f.device))
+    if rc == L.MSS_ERR_UNSUPPORTED:
+        raise L.MssError("m2f.mask_logits: " + L.last_error())
+    L.check(rc, "mss_m2f_mask_logits")
+    return out
+
+
+def anomaly_score_from_features(pred_logits_ood: torch.Tensor, mask_embed: torch.Tensor, mask_features: torch.Tensor,
+                                padded_size: Sequence[int], size: Sequence[int]) -> torch.Tensor:
+    """mask2former_transformer_decoder.py:548-549 + maskformer_model.py:271-277 + train_m2f.py:387-407 in two
+    launches: mask-logit GEMM (decoder-resolution masks written once, 52 MB per 1024 x 2048 image), then the fused
+    upsample / sigmoid / contraction / 1 - max kernel.  The [B, Q, H, W] tensors never exist."""
+    return anomaly_score_from_lowres(pred_logits_ood, mask_logits(mask_embed, mask_features), padded_size, size)

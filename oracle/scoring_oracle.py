@@ -106,3 +106,10 @@ def m2f_anomaly_from_lowres(pred_logits_ood, pred_masks_ood_lowres, padded_size,
     """maskformer_model.py:271-277 + train_m2f.py:387-407 in sequence."""
     up = upsample_masks(pred_masks_ood_lowres, padded_size)
     return get_anomaly_score({"pred_logits_ood": pred_logits_ood, "pred_masks_ood": up}, image_size)
+
+
+def m2f_mask_logits(mask_embed: torch.Tensor, mask_features: torch.Tensor) -> torch.Tensor:
+    """lib/network/mask2former/modeling/transformer_decoder/mask2former_transformer_decoder.py:529 and :549
+    (SURVEY 8f-1): ``outputs_mask = torch.einsum("bqc,bchw->bqhw", mask_embed, mask_features)``.  The op is
+    torch's own; no reference-generated fixture (the line sits inside the decoder ``forward``)."""
+    return torch.einsum("bqc,bchw->bqhw", mask_embed, mask_features)
