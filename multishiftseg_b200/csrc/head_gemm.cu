@@ -73,7 +73,10 @@ head_gemm_kernel(const float *__restrict__ feat, long long hw, int K, int C, lon
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 8);
     uint64_t *bar_full = s_bar, *bar_empty = s_bar + 2, *bar_dfull = s_bar + 4;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index through a shuffle: ptxas then knows it is warp-uniform, keeps the role branches uniform (BRA.U) and
+    // the load descriptors / loop state in uniform registers instead of re-materialising them (R2UR) at every load
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int stages = K / HG_STAGE_K;
 
     if (tid == HG_PRODUCERS) {
@@ -160,16 +163,19 @@ head_gemm_kernel(const float *__restrict__ feat, long long hw, int K, int C, lon
         for (long long it = 0; it < my_tiles; it++) {
             const long long tile = (long long)blockIdx.x + it * gridDim.x;
             const long long b = tile / tiles_per_image, p = (tile - b * tiles_per_image) * 128 + m;
-            const bool live = p < hw;
-            const float *src = feat + (b * K + half * 16) * hw + (live ? p : 0);
+            // One running pointer per tile, advanced by a plane per load (rows past the end read the last pixel; their
+            // results are never stored).  The first form, `live ? ld(src + j * hw) : 0`, cost ~8 instructions of predicated
+            // 64-bit address arithmetic per load (SASS, round 1).
+            const char *q = reinterpret_cast<const char *>(feat + (b * K + half * 16) * hw + (p < hw ? p : hw - 1));
+            const size_t plane = (size_t)hw * sizeof(float);
             float cur[16], nxt[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) cur[j] = live ? ldg_stream_f1(src + (long long)j * hw) : 0.f;
+            for (int j = 0; j < 16; j++) { cur[j] = ldg_stream_f1(reinterpret_cast<const float *>(q)); q += plane; }
             for (int s = 0; s < stages; s++, u++) {
                 if (s + 1 < stages) {
-                    const float *q = src + (long long)(s + 1) * HG_STAGE_K * hw;
+                    q += 16 * plane;                                             // the other half's channels
 #pragma unroll
-                    for (int j = 0; j < 16; j++) nxt[j] = live ? ldg_stream_f1(q + (long long)j * hw) : 0.f;
+                    for (int j = 0; j < 16; j++) { nxt[j] = ldg_stream_f1(reinterpret_cast<const float *>(q)); q += plane; }
                 }
                 uint32_t hi[16], lo[16];
 #pragma unroll

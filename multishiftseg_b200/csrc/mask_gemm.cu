@@ -54,14 +54,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 
 __global__ void __launch_bounds__(MG_THREADS, 1)
 mask_gemm_kernel(const float *__restrict__ feat, int hw, int K, int Q, long long n_items, int slices,
-                 long long tiles_per_image, const float *__restrict__ table, float *__restrict__ out) {
+                 int tiles_per_image, const float *__restrict__ table, float *__restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_b = reinterpret_cast<float *>(smem_raw);                            // [hi | lo][K/4][112][4]
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_b + 2 * K * MG_N);          // per group: full[2] empty[2] dfull dempty; + table
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 16);
     uint64_t *bar_table = s_bar + 12;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index through a shuffle: ptxas then knows it is warp-uniform, keeps the role branches uniform (BRA.U) and
+    // the load descriptors / loop state in uniform registers instead of re-materialising them (R2UR) at every load
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int stages = K / MG_STAGE_K;
     const unsigned table_bytes = (unsigned)(2 * K * MG_N * 4);
 
@@ -98,11 +101,11 @@ mask_gemm_kernel(const float *__restrict__ feat, int hw, int K, int Q, long long
         const uint32_t col_d = (uint32_t)g * 128, col_a = 256 + (uint32_t)g * 128;
         uint64_t *bar_full = s_bar + 6 * g, *bar_empty = bar_full + 2, *bar_dfull = bar_full + 4, *bar_dempty = bar_full + 5;
 
-        long long u = 0, done = 0;                                               // stage uses / finished epilogues (whole kernel)
+        unsigned u = 0, done = 0;                                                // stage uses / finished epilogues (whole kernel; only parities matter)
         for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
             const long long b = item / slices;
             const int slice = (int)(item - b * slices);
-            const long long n_j = (tiles_per_image > slice) ? (tiles_per_image - slice + slices - 1) / slices : 0;
+            const int n_j = (tiles_per_image > slice) ? (tiles_per_image - slice + slices - 1) / slices : 0;
             // offsets inside one image fit 32 bits (host-checked: K * hw, Q * hw < 2^31): fewer 64-bit registers
             const float *fimg = feat + (b * K + half * 16) * (long long)hw;
             float *oimg = out + (b * Q + half * MG_HALF_N) * (long long)hw;
@@ -112,16 +115,18 @@ mask_gemm_kernel(const float *__restrict__ feat, int hw, int K, int Q, long long
                 mbar_wait(bar_dfull, (unsigned)(done & 1));
                 tc5_fence_after();
                 const uint32_t d = lane_base + col_d + half * MG_HALF_N;
-                float *o = oimg + p;
+                float *o = oimg + (p < hw ? p : 0);
+                const int ncols = (p < hw) ? min(MG_HALF_N, Q - half * MG_HALF_N) : 0;     // query planes this thread stores
+                const size_t plane = (size_t)(unsigned)hw * sizeof(float);
 #pragma unroll
                 for (int c0 = 0; c0 < MG_HALF_N; c0 += 8) {
                     uint32_t v[8];
                     tc5_ld8(d + c0, v);
                     tc5_wait_ld();
-                    if (p < hw) {
 #pragma unroll
-                        for (int c = 0; c < 8; c++)
-                            if (half * MG_HALF_N + c0 + c < Q) o[(unsigned)((c0 + c) * hw)] = __uint_as_float(v[c]);
+                    for (int c = 0; c < 8; c++) {
+                        if (c0 + c < ncols) *o = __uint_as_float(v[c]);
+                        o = reinterpret_cast<float *>(reinterpret_cast<char *>(o) + plane);
                     }
                 }
                 tc5_fence_before();
@@ -130,38 +135,51 @@ mask_gemm_kernel(const float *__restrict__ feat, int hw, int K, int Q, long long
             };
 
             int p_prev = -1;
-            for (long long j = g; j < n_j; j += 2) {
-                const long long p64 = ((long long)slice + j * slices) * 128 + m;
-                const int p = (int)(p64 < hw ? p64 : hw);   // hw = "past the end"
-                const bool live = p < hw;
-                const float *src = fimg + (live ? p : 0);
+            for (int j = g; j < n_j; j += 2) {
+                const long long p64 = ((long long)slice + (long long)j * slices) * 128 + m;
+                const int p = (int)(p64 < hw ? p64 : hw);   // hw = "past the end": loads are clamped, stores skipped
+                // One running pointer per tile, advanced by a plane per load: 2 instructions per element.  (First form:
+                // `live ? ld(src + i * hw) : 0` -- ncu/SASS showed ~8 instructions of predicated 64-bit address
+                // arithmetic per load, 21 warp instructions per element in total, issue slots 50 % busy with 4.5 warps
+                // per scheduler: the kernel was issue/latency-bound at 4.0 TB/s.)
+                const float *q = fimg + (p < hw ? p : hw - 1);
+                const size_t plane = (size_t)(unsigned)hw * sizeof(float);
                 float cur[16], nxt[16];
 #pragma unroll
-                for (int i = 0; i < 16; i++) cur[i] = live ? ldg_stream_f1(src + (unsigned)(i * hw)) : 0.f;
+                for (int i = 0; i < 16; i++) {
+                    cur[i] = ldg_stream_f1(q);
+                    q = reinterpret_cast<const float *>(reinterpret_cast<const char *>(q) + plane);
+                }
+                // the previous tile's epilogue runs here, behind this tile's first 16 loads and before the stage-1 loads
+                // are issued: no second register buffer is live across it (inside the stage loop it spilled `nxt`)
+                if (p_prev >= 0) epilogue(p_prev);
                 for (int s = 0; s < stages; s++, u++) {
                     if (s + 1 < stages) {
-                        const float *q = src + (unsigned)((s + 1) * MG_STAGE_K * hw);
+                        q = reinterpret_cast<const float *>(reinterpret_cast<const char *>(q) + 16 * plane);   // the other half's channels
 #pragma unroll
-                        for (int i = 0; i < 16; i++) nxt[i] = live ? ldg_stream_f1(q + (unsigned)(i * hw)) : 0.f;
-                    }
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        hi[i] = __float_as_uint(cur[i]) & 0xFFFFE000u;
-                        lo[i] = __float_as_uint(cur[i] - __uint_as_float(hi[i]));
+                        for (int i = 0; i < 16; i++) {
+                            nxt[i] = ldg_stream_f1(q);
+                            q = reinterpret_cast<const float *>(reinterpret_cast<const char *>(q) + plane);
+                        }
                     }
                     const int slot = (int)(u & 1);
                     if (u >= 2) mbar_wait(&bar_empty[slot], (unsigned)(((u >> 1) + 1) & 1));   // MMAs of use u-2 are done
                     tc5_fence_after();
                     const uint32_t a = lane_base + col_a + slot * 64 + half * 16;
-                    tc5_st16(a, hi);
-                    tc5_st16(a + 32, lo);
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {                                // 8 channels at a time: 16 temporaries, not 32
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            hi[i] = __float_as_uint(cur[8 * c + i]) & 0xFFFFE000u;
+                            lo[i] = __float_as_uint(cur[8 * c + i] - __uint_as_float(hi[i]));
+                        }
+                        tc5_st8(a + 8 * c, hi);
+                        tc5_st8(a + 32 + 8 * c, lo);
+                    }
                     tc5_wait_st();
                     tc5_fence_before();
                     mbar_arrive(&bar_full[slot]);
-                    // the previous tile's epilogue, one stage late: stage 1 of this tile is already in flight, and
-                    // the issuer holds this tile's first MMA until the accumulator has been read
-                    if (s == 0 && p_prev >= 0) epilogue(p_prev);
 #pragma unroll
                     for (int i = 0; i < 16; i++) cur[i] = nxt[i];
                 }
@@ -176,11 +194,11 @@ mask_gemm_kernel(const float *__restrict__ feat, int hw, int K, int Q, long long
         const uint32_t bhi = smem_u32(s_b), blo = bhi + (uint32_t)K * MG_N * 4;
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);               // warp-uniform (see m2f_tc5q.cuh)
         const uint32_t d = tmem_u + (uint32_t)g * 128, col_a = tmem_u + 256 + (uint32_t)g * 128;
-        long long u = 0, done = 0, n_loaded = 0;
+        unsigned u = 0, done = 0, n_loaded = 0;
         for (long long item = blockIdx.x; item < n_items; item += gridDim.x, n_loaded++) {
             const long long b = item / slices;
             const int slice = (int)(item - b * slices);
-            const long long n_j = (tiles_per_image > slice) ? (tiles_per_image - slice + slices - 1) / slices : 0;
+            const int n_j = (tiles_per_image > slice) ? (tiles_per_image - slice + slices - 1) / slices : 0;
             // the image's table: every MMA of both groups that read the previous one has completed
             if (n_loaded > 0) {
                 if (done > 0) mbar_wait_backoff(bar_dfull, (unsigned)((done - 1) & 1), 32);
@@ -192,7 +210,7 @@ mask_gemm_kernel(const float *__restrict__ feat, int hw, int K, int Q, long long
             }
             __syncwarp();
             mbar_wait_backoff(bar_table, (unsigned)(n_loaded & 1), 32);
-            for (long long j = g; j < n_j; j += 2, done++) {
+            for (int j = g; j < n_j; j += 2, done++) {
                 for (int s = 0; s < stages; s++, u++) {
                     const int slot = (int)(u & 1);
                     mbar_wait_backoff(&bar_full[slot], (unsigned)((u >> 1) & 1), 32);
@@ -268,10 +286,10 @@ extern "C" int mss_m2f_mask_logits(const float *mask_embed, const float *mask_fe
                                             (int)mask_gemm_smem(MG_MAX_K)));
         attr_set.store(true);
     }
-    const long long tiles_per_image = (hw + 127) / 128;
+    const int tiles_per_image = (int)((hw + 127) / 128);
     const int sms = sm_count();
     // B <= SMs: S = SMs / B slices per image, one work item per CTA; otherwise whole images, round-robin
-    int slices = (B <= sms) ? (int)std::min<long long>(tiles_per_image, (long long)(sms / (int)B)) : 1;
+    int slices = (B <= sms) ? std::min(tiles_per_image, sms / (int)B) : 1;
     if (slices < 1) slices = 1;
     const long long n_items = (long long)B * slices;
     const int grid = (int)std::min<long long>(n_items, (long long)sms);

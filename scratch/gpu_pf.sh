@@ -1,0 +1,5 @@
+#!/bin/bash
+O=gpurun_out; mkdir -p $O
+echo "== prefetch on"; timeout 200 python scratch/bench_maskgemm.py 2>&1 | head -1; timeout 200 python scratch/bench_head.py 2>&1 | head -1
+echo "== prefetch off"; MSS_NO_L2_PREFETCH=1 timeout 200 python scratch/bench_maskgemm.py 2>&1 | head -1; MSS_NO_L2_PREFETCH=1 timeout 200 python scratch/bench_head.py 2>&1 | head -1
+timeout 300 python -m pytest tests/test_gpu_maskgemm.py tests/test_gpu_head.py -x -q 2>&1 | tail -3
