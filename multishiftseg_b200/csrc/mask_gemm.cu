@@ -9,28 +9,41 @@
 // with the feature values loaded coalesced (lane <-> pixel <-> TMEM lane), split in registers and written
 // straight into TENSOR MEMORY as the A operand; the pre-split embedding table of the image is the B operand.
 //
-// What differs from the DeepLab head: the B table is 2 x 112 x 256 x 4 B = 224 KB -- one CTA per SM, all of its
-// shared memory -- and it changes with the image.  So a CTA is TWO independent pipelines ("groups", each the
-// producer / issuer / epilogue structure of head_gemm.cu on its own 128-pixel tiles) sharing one B table:
-//   * warps 0-7 / 8-15: producers + epilogue of group 0 / 1; warp 16 / 17: MMA issuer of group 0 / 1;
+// The B table is 2 x 112 x 256 x 4 B = 224 KB -- one CTA per SM, all of its shared memory, nothing left to stage
+// features in -- and it changes with the image.  The feature tile therefore waits in REGISTERS:
+//   * 8 producer warps + 1 MMA-issuer warp (288 threads, ~200 registers each); tile = 128 pixels, stage = 32
+//     channels (a thread's half takes 16 of them);
+//   * a thread keeps a ring of 6 x 16 loaded values (96 registers; three quarters of a K = 256 tile): right after a
+//     stage has been split and stored to TMEM, the loads of the stage 6 positions later -- the rest of this tile, then
+//     the next one -- are issued into the same registers, so every load has ~6 us to arrive and ~90 KB per SM are
+//     in flight.
+//     (v1 of this kernel, two 8-warp pipelines with a 2-deep register buffer at 96 registers/thread: 0.357 ms for the
+//     cfg-3 batch, 41 % of all stall samples on the first use of a loaded value, DRAM 47 %, tensor pipe 50 % -- the
+//     load latency and the tensor work added up instead of overlapping.)
+//   * 4 A slots in TMEM (64 columns each: 32 hi + 32 lo), two accumulators (112 columns each) -> all 512 columns;
 //   * work item = (image, slice): a CTA keeps one image's table and walks tiles slice, slice + S, ... of that
-//     image (S = SMs / B slices per image when B <= SMs: one item per CTA, ~1000/S tiles each);
-//   * the table arrives as ONE 224 KB bulk copy (cp.async.bulk -> mbarrier), issued by the MMA warps once both
-//     groups' tensor work of the previous item has completed;
-//   * TMEM (all 512 columns): accumulators D_g at g*128 (112 columns), A buffers at 256 + g*128 + slot*64.
-//     One accumulator per group: the epilogue of a tile runs before the group's next tile is staged (the other
-//     group keeps the memory system busy meanwhile); the next tile's first 16 loads are already in flight.
-//   * epilogue: half h of a lane quarter stores query planes 56h .. 56h+55 (< Q): 128-byte coalesced rows.
+//     image (S = SMs / B slices per image when B <= SMs: one item per CTA); the table arrives as ONE 224 KB bulk
+//     copy (cp.async.bulk -> mbarrier) issued by the MMA warp once the tensor work of the previous item is complete;
+//     the producers never touch it and prefetch straight across item boundaries;
+//   * epilogue of tile t: 7 chunks of 8 accumulator columns, one chunk after each stage of tile t+1 (half h of a lane
+//     quarter stores query planes 56h .. 56h+55 (< Q): 128-byte coalesced rows).
+// Addresses: one running pointer per tile, advanced by a plane per load (2 instructions per element); warp index
+// through a shuffle so that ptxas keeps the role branches and descriptors uniform.
+#include <type_traits>
+
 #include "tc5_common.cuh"
 
 namespace mss {
 
 constexpr int MG_N = 112;                          // queries padded: UMMA N % 16 == 0 for M = 128
 constexpr int MG_HALF_N = MG_N / 2;                // columns per epilogue half
+constexpr int MG_CHUNKS = MG_HALF_N / 8;           // epilogue chunks of 8 columns
 constexpr int MG_STAGE_K = 32;
-constexpr int MG_GROUP_THREADS = 256;              // producer threads per group
-constexpr int MG_THREADS = 2 * MG_GROUP_THREADS + 64;
+constexpr int MG_PRODUCERS = 256;
+constexpr int MG_THREADS = MG_PRODUCERS + 32;
+constexpr int MG_SLOTS = 4;
 constexpr int MG_TMEM_COLS = 512;
+constexpr int MG_COL_A = 256;                      // D buffers at 0 and 128, A slot k at 256 + 64 k
 constexpr int MG_MAX_K = 256;
 constexpr uint32_t MG_IDESC = tc5_idesc_tf32(128, MG_N);
 
@@ -48,41 +61,56 @@ __global__ void mask_embed_umma_kernel(const float *__restrict__ embed, int Q, i
     t[K * MG_N + o] = w - hi;
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
+// the CTA's flat tile sequence: items blockIdx.x, + gridDim.x, ...; inside item (image b, slice): tiles slice + j * slices
+struct TileCursor {
+    long long item, n_items, b;
+    int slices, tiles_per_image, slice, j, n_j;
+    __device__ __forceinline__ void set_item() {
+        b = item / slices;
+        slice = (int)(item - b * slices);
+        n_j = (tiles_per_image - slice + slices - 1) / slices;      // >= 1: the host keeps slices <= tiles_per_image
+        j = 0;
+    }
+    __device__ __forceinline__ TileCursor(long long first, long long n_items_, int slices_, int tpi)
+        : item(first), n_items(n_items_), b(0), slices(slices_), tiles_per_image(tpi), slice(0), j(0), n_j(0) {
+        if (item < n_items) set_item();
+    }
+    __device__ __forceinline__ bool valid() const { return item < n_items; }
+    __device__ __forceinline__ long long first_pixel() const { return ((long long)slice + (long long)j * slices) * 128; }
+    __device__ __forceinline__ void next() {
+        if (++j >= n_j) {
+            item += gridDim.x;
+            if (item < n_items) set_item();
+        }
+    }
+};
 
+template <int STAGES>
 __global__ void __launch_bounds__(MG_THREADS, 1)
-mask_gemm_kernel(const float *__restrict__ feat, int hw, int K, int Q, long long n_items, int slices,
-                 int tiles_per_image, const float *__restrict__ table, float *__restrict__ out) {
+mask_gemm_kernel(const float *__restrict__ feat, int hw, int Q, long long n_items, int slices, int tiles_per_image,
+                 const float *__restrict__ table, float *__restrict__ out) {
+    constexpr int K = STAGES * MG_STAGE_K;
+    constexpr int CPS = (MG_CHUNKS + STAGES - 1) / STAGES;                       // epilogue chunks per stage
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_b = reinterpret_cast<float *>(smem_raw);                            // [hi | lo][K/4][112][4]
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_b + 2 * K * MG_N);          // per group: full[2] empty[2] dfull dempty; + table
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_b + 2 * K * MG_N);          // full[4] empty[4] dfull[2] dempty[2] table
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 16);
-    uint64_t *bar_table = s_bar + 12;
+    uint64_t *bar_full = s_bar, *bar_empty = s_bar + 4, *bar_dfull = s_bar + 8, *bar_dempty = s_bar + 10, *bar_table = s_bar + 12;
 
     const int tid = threadIdx.x, lane = tid & 31;
     // warp index through a shuffle: ptxas then knows it is warp-uniform, keeps the role branches uniform (BRA.U) and
     // the load descriptors / loop state in uniform registers instead of re-materialising them (R2UR) at every load
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int stages = K / MG_STAGE_K;
-    const unsigned table_bytes = (unsigned)(2 * K * MG_N * 4);
+    constexpr unsigned table_bytes = 2u * K * MG_N * 4u;
 
-    if (tid == 2 * MG_GROUP_THREADS) {
-        for (int g = 0; g < 2; g++) {
-            uint64_t *bg = s_bar + 6 * g;
-            mbar_init(&bg[0], MG_GROUP_THREADS);
-            mbar_init(&bg[1], MG_GROUP_THREADS);
-            mbar_init(&bg[2], 1);
-            mbar_init(&bg[3], 1);
-            mbar_init(&bg[4], 1);
-            mbar_init(&bg[5], MG_GROUP_THREADS);
-        }
+    if (tid == MG_PRODUCERS) {
+        for (int k = 0; k < MG_SLOTS; k++) { mbar_init(&bar_full[k], MG_PRODUCERS); mbar_init(&bar_empty[k], 1); }
+        for (int k = 0; k < 2; k++) { mbar_init(&bar_dfull[k], 1); mbar_init(&bar_dempty[k], MG_PRODUCERS); }
         mbar_init(bar_table, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 16) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
                      "n"(MG_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -92,152 +120,183 @@ mask_gemm_kernel(const float *__restrict__ feat, int hw, int K, int Q, long long
     tc5_fence_after();
     const uint32_t tmem = *s_tmem;
 
-    if (warp < 16) {
-        // ===== producers + epilogue of group g =====
-        const int g = warp >> 3, wg = warp & 7;
-        const int quarter = wg & 3, half = wg >> 2;
+    if (warp < 8) {
+        // ===== producers + epilogue =====
+        const int quarter = warp & 3, half = warp >> 2;
         const int m = quarter * 32 + lane;                                       // pixel inside the tile == TMEM lane
         const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t col_d = (uint32_t)g * 128, col_a = 256 + (uint32_t)g * 128;
-        uint64_t *bar_full = s_bar + 6 * g, *bar_empty = bar_full + 2, *bar_dfull = bar_full + 4, *bar_dempty = bar_full + 5;
+        const size_t plane = (size_t)(unsigned)hw * sizeof(float);
+        const int my_cols = min(MG_HALF_N, Q - half * MG_HALF_N);                // query planes this thread stores (may be <= 0)
 
-        unsigned u = 0, done = 0;                                                // stage uses / finished epilogues (whole kernel; only parities matter)
-        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const long long b = item / slices;
-            const int slice = (int)(item - b * slices);
-            const int n_j = (tiles_per_image > slice) ? (tiles_per_image - slice + slices - 1) / slices : 0;
-            // offsets inside one image fit 32 bits (host-checked: K * hw, Q * hw < 2^31): fewer 64-bit registers
-            const float *fimg = feat + (b * K + half * 16) * (long long)hw;
-            float *oimg = out + (b * Q + half * MG_HALF_N) * (long long)hw;
+        // Register ring of RING stage buffers: the loads of flat stage k + RING are issued right after stage k has been
+        // consumed, into the same registers.  For K = 256 (8 stages per tile) RING = 6: ~88 loads per thread in flight,
+        // three quarters of a tile ahead; the ring position of a tile's first stage cycles through 0, 2, 4, so the tile
+        // loop is unrolled three times (static register indices).  (RING = 8 needs 183 registers; 288 threads are
+        // allocated as 12 warps, i.e. 168 registers per thread at most -- it spilled freshly loaded values.)
+        constexpr int RING = (STAGES == 8) ? 6 : STAGES;
+        constexpr int LAG = STAGES - RING;                                      // stages of the SAME tile still to prefetch
+        float buf[RING][16];
+        const char *qn = nullptr;                                                // running load pointer (tile being prefetched)
+        char *o_cur = nullptr, *o_prev = nullptr, *o_next = nullptr;             // first output plane of a tile (null: row past the end)
+        unsigned u = 0, t = 0;                                                   // stage uses / tiles so far (only parities matter)
+        bool have_next = false, have_prev = false;
 
-            // epilogue of the tile whose first pixel row is `p`: columns 56*half .. 56*half + 55 of this lane's row
-            auto epilogue = [&](int p) {
-                mbar_wait(bar_dfull, (unsigned)(done & 1));
-                tc5_fence_after();
-                const uint32_t d = lane_base + col_d + half * MG_HALF_N;
-                float *o = oimg + (p < hw ? p : 0);
-                const int ncols = (p < hw) ? min(MG_HALF_N, Q - half * MG_HALF_N) : 0;     // query planes this thread stores
-                const size_t plane = (size_t)(unsigned)hw * sizeof(float);
+        TileCursor pf(blockIdx.x, n_items, slices, tiles_per_image);
+        // thread's load pointer and output pointer for the cursor's tile
+        auto setup = [&](const TileCursor &c, char *&o) {
+            const long long p = c.first_pixel() + m;
+            const long long pc = p < hw ? p : (long long)hw - 1;                 // rows past the end read the last pixel
+            qn = reinterpret_cast<const char *>(feat + (c.b * K + half * 16) * (long long)hw + pc);
+            o = (p < hw) ? reinterpret_cast<char *>(out + (c.b * Q + half * MG_HALF_N) * (long long)hw + p) : nullptr;
+        };
+        auto load_stage = [&](float (&dst)[16]) {
 #pragma unroll
-                for (int c0 = 0; c0 < MG_HALF_N; c0 += 8) {
-                    uint32_t v[8];
-                    tc5_ld8(d + c0, v);
-                    tc5_wait_ld();
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        if (c0 + c < ncols) *o = __uint_as_float(v[c]);
-                        o = reinterpret_cast<float *>(reinterpret_cast<char *>(o) + plane);
-                    }
-                }
-                tc5_fence_before();
-                mbar_arrive(bar_dempty);                                         // the accumulator may be overwritten
-                done++;
-            };
-
-            int p_prev = -1;
-            for (int j = g; j < n_j; j += 2) {
-                const long long p64 = ((long long)slice + (long long)j * slices) * 128 + m;
-                const int p = (int)(p64 < hw ? p64 : hw);   // hw = "past the end": loads are clamped, stores skipped
-                // One running pointer per tile, advanced by a plane per load: 2 instructions per element.  (First form:
-                // `live ? ld(src + i * hw) : 0` -- ncu/SASS showed ~8 instructions of predicated 64-bit address
-                // arithmetic per load, 21 warp instructions per element in total, issue slots 50 % busy with 4.5 warps
-                // per scheduler: the kernel was issue/latency-bound at 4.0 TB/s.)
-                const float *q = fimg + (p < hw ? p : hw - 1);
-                const size_t plane = (size_t)(unsigned)hw * sizeof(float);
-                float cur[16], nxt[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    cur[i] = ldg_stream_f1(q);
-                    q = reinterpret_cast<const float *>(reinterpret_cast<const char *>(q) + plane);
-                }
-                // the previous tile's epilogue runs here, behind this tile's first 16 loads and before the stage-1 loads
-                // are issued: no second register buffer is live across it (inside the stage loop it spilled `nxt`)
-                if (p_prev >= 0) epilogue(p_prev);
-                for (int s = 0; s < stages; s++, u++) {
-                    if (s + 1 < stages) {
-                        q = reinterpret_cast<const float *>(reinterpret_cast<const char *>(q) + 16 * plane);   // the other half's channels
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            nxt[i] = ldg_stream_f1(q);
-                            q = reinterpret_cast<const float *>(reinterpret_cast<const char *>(q) + plane);
-                        }
-                    }
-                    const int slot = (int)(u & 1);
-                    if (u >= 2) mbar_wait(&bar_empty[slot], (unsigned)(((u >> 1) + 1) & 1));   // MMAs of use u-2 are done
-                    tc5_fence_after();
-                    const uint32_t a = lane_base + col_a + slot * 64 + half * 16;
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {                                // 8 channels at a time: 16 temporaries, not 32
-                        uint32_t hi[8], lo[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            hi[i] = __float_as_uint(cur[8 * c + i]) & 0xFFFFE000u;
-                            lo[i] = __float_as_uint(cur[8 * c + i] - __uint_as_float(hi[i]));
-                        }
-                        tc5_st8(a + 8 * c, hi);
-                        tc5_st8(a + 32 + 8 * c, lo);
-                    }
-                    tc5_wait_st();
-                    tc5_fence_before();
-                    mbar_arrive(&bar_full[slot]);
-#pragma unroll
-                    for (int i = 0; i < 16; i++) cur[i] = nxt[i];
-                }
-                p_prev = p;
+            for (int i = 0; i < 16; i++) {
+                dst[i] = ldg_stream_f1(reinterpret_cast<const float *>(qn));
+                qn += plane;
+                asm volatile("" : "+l"(qn));     // keep ONE running pointer (ptxas otherwise precomputes and spills dozens)
             }
-            if (p_prev >= 0) epilogue(p_prev);
+            qn += 16 * plane;                                                    // the other half's channels
+            asm volatile("" : "+l"(qn));
+        };
+        // chunk c of the epilogue of tile t-1 (accumulator (t-1) & 1): 8 columns -> 8 query planes
+        auto epi_chunk = [&](int c) {
+            const unsigned tp = t - 1, db = tp & 1;
+            if (c == 0) {
+                mbar_wait(&bar_dfull[db], (tp >> 1) & 1);
+                tc5_fence_after();
+            }
+            uint32_t v[8];
+            tc5_ld8(lane_base + db * 128 + half * MG_HALF_N + c * 8, v);
+            tc5_wait_ld();
+            if (o_prev) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (c * 8 + i < my_cols) *reinterpret_cast<float *>(o_prev) = __uint_as_float(v[i]);
+                    o_prev += plane;
+                    asm volatile("" : "+l"(o_prev));
+                }
+            }
+            if (c == MG_CHUNKS - 1) {
+                tc5_fence_before();
+                mbar_arrive(&bar_dempty[db]);                                    // the accumulator may be overwritten
+            }
+        };
+        // one tile whose first stage sits at ring position OFF
+        auto tile_body = [&](auto off_c) {
+            constexpr int OFF = decltype(off_c)::value;
+#pragma unroll
+            for (int s = 0; s < STAGES; s++, u++) {
+                float (&cur)[16] = buf[(OFF + s) % RING];
+                const unsigned slot = u & (MG_SLOTS - 1);
+                if (u >= MG_SLOTS) mbar_wait(&bar_empty[slot], ((u >> 2) + 1) & 1);   // MMAs of use u-4 are done
+                tc5_fence_after();
+                const uint32_t a = lane_base + MG_COL_A + slot * 64 + half * 16;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {                                    // 8 channels at a time: 16 temporaries
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        hi[i] = __float_as_uint(cur[8 * c + i]) & 0xFFFFE000u;
+                        lo[i] = __float_as_uint(cur[8 * c + i] - __uint_as_float(hi[i]));
+                    }
+                    tc5_st8(a + 8 * c, hi);
+                    tc5_st8(a + 32 + 8 * c, lo);
+                }
+                tc5_wait_st();
+                tc5_fence_before();
+                mbar_arrive(&bar_full[slot]);
+                // flat stage + RING: the rest of this tile first, then the next tile
+                if (s < LAG) load_stage(cur);
+                else {
+                    if (s == LAG) {
+                        have_next = pf.valid();
+                        if (have_next) { setup(pf, o_next); pf.next(); }
+                    }
+                    if (have_next) load_stage(cur);
+                }
+                if (have_prev) {
+#pragma unroll
+                    for (int c = s * CPS; c < (s + 1) * CPS && c < MG_CHUNKS; c++) epi_chunk(c);
+                }
+            }
+            t++;
+            o_prev = o_cur;
+            have_prev = true;
+            o_cur = o_next;
+        };
+
+        bool have = pf.valid();
+        if (have) {
+            setup(pf, o_cur);
+            pf.next();
+#pragma unroll
+            for (int s = 0; s < RING; s++) load_stage(buf[s]);
+        }
+        while (have) {
+            tile_body(std::integral_constant<int, 0>{});
+            have = have_next;
+            if (STAGES % RING != 0) {                                            // K = 256: ring positions 0, 2, 4
+                if (!have) break;
+                tile_body(std::integral_constant<int, (STAGES) % RING>{});
+                have = have_next;
+                if (!have) break;
+                tile_body(std::integral_constant<int, (2 * STAGES) % RING>{});
+                have = have_next;
+            }
+        }
+        if (have_prev) {
+#pragma unroll
+            for (int c = 0; c < MG_CHUNKS; c++) epi_chunk(c);
         }
     } else {
-        // ===== MMA issuer of group g: the whole warp waits (stays converged), one elected lane issues =====
-        const int g = warp - 16;
-        uint64_t *bar_full = s_bar + 6 * g, *bar_empty = bar_full + 2, *bar_dfull = bar_full + 4, *bar_dempty = bar_full + 5;
+        // ===== MMA issuer: the whole warp waits (stays converged), one elected lane issues =====
         const uint32_t bhi = smem_u32(s_b), blo = bhi + (uint32_t)K * MG_N * 4;
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);               // warp-uniform (see m2f_tc5q.cuh)
-        const uint32_t d = tmem_u + (uint32_t)g * 128, col_a = tmem_u + 256 + (uint32_t)g * 128;
-        unsigned u = 0, done = 0, n_loaded = 0;
-        for (long long item = blockIdx.x; item < n_items; item += gridDim.x, n_loaded++) {
-            const long long b = item / slices;
-            const int slice = (int)(item - b * slices);
-            const int n_j = (tiles_per_image > slice) ? (tiles_per_image - slice + slices - 1) / slices : 0;
-            // the image's table: every MMA of both groups that read the previous one has completed
-            if (n_loaded > 0) {
-                if (done > 0) mbar_wait_backoff(bar_dfull, (unsigned)((done - 1) & 1), 32);
-                named_bar_sync(1, 64);
-            }
-            if (g == 0 && elect_one_sync()) {
-                mbar_expect_tx(bar_table, table_bytes);
-                bulk_load_1d(s_b, table + b * 2 * K * MG_N, table_bytes, bar_table);
-            }
-            __syncwarp();
-            mbar_wait_backoff(bar_table, (unsigned)(n_loaded & 1), 32);
-            for (int j = g; j < n_j; j += 2, done++) {
-                for (int s = 0; s < stages; s++, u++) {
-                    const int slot = (int)(u & 1);
-                    mbar_wait_backoff(&bar_full[slot], (unsigned)((u >> 1) & 1), 32);
-                    if (s == 0 && done > 0) mbar_wait_backoff(bar_dempty, (unsigned)((done - 1) & 1), 32);   // epilogue has read the tile before
-                    tc5_fence_after();
-                    if (elect_one_sync()) {
-#pragma unroll
-                        for (int kk = 0; kk < MG_STAGE_K / 8; kk++) {
-                            const int ks = s * (MG_STAGE_K / 8) + kk;            // k-step of 8 channels = 2 core-matrix chunks
-                            const uint64_t dh = tc5_smem_desc(bhi + ks * 2 * (MG_N * 16), MG_N * 16, 128);
-                            const uint64_t dl = tc5_smem_desc(blo + ks * 2 * (MG_N * 16), MG_N * 16, 128);
-                            const uint32_t ahi = col_a + slot * 64 + kk * 8, alo = ahi + 32;
-                            tc5_mma_ts(d, alo, dh, MG_IDESC, (s | kk) > 0);
-                            tc5_mma_ts(d, ahi, dl, MG_IDESC, 1);
-                            tc5_mma_ts(d, ahi, dh, MG_IDESC, 1);
-                        }
-                        tc5_commit(&bar_empty[slot]);
-                        if (s == stages - 1) tc5_commit(bar_dfull);
-                    }
-                    __syncwarp();
+        unsigned u = 0, t = 0, n_loaded = 0;
+        long long cur_item = -1;
+        for (TileCursor c(blockIdx.x, n_items, slices, tiles_per_image); c.valid(); c.next(), t++) {
+            if (c.item != cur_item) {
+                // the image's table: every MMA that read the previous one has completed (commits are in order)
+                if (t > 0) mbar_wait_backoff(&bar_dfull[(t - 1) & 1], ((t - 1) >> 1) & 1, 32);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(bar_table, table_bytes);
+                    bulk_load_1d(s_b, table + c.b * 2 * K * MG_N, table_bytes, bar_table);
                 }
+                __syncwarp();
+                mbar_wait_backoff(bar_table, n_loaded & 1, 32);
+                n_loaded++;
+                cur_item = c.item;
+            }
+            const unsigned db = t & 1;
+            if (t >= 2) mbar_wait_backoff(&bar_dempty[db], ((t >> 1) + 1) & 1, 32);   // epilogue of tile t-2 has read this accumulator
+            const uint32_t d = tmem_u + db * 128;
+#pragma unroll 1
+            for (int s = 0; s < STAGES; s++, u++) {
+                const unsigned slot = u & (MG_SLOTS - 1);
+                mbar_wait_backoff(&bar_full[slot], (u >> 2) & 1, 32);
+                tc5_fence_after();
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int kk = 0; kk < MG_STAGE_K / 8; kk++) {
+                        const int ks = s * (MG_STAGE_K / 8) + kk;                // k-step of 8 channels = 2 core-matrix chunks
+                        const uint64_t dh = tc5_smem_desc(bhi + ks * 2 * (MG_N * 16), MG_N * 16, 128);
+                        const uint64_t dl = tc5_smem_desc(blo + ks * 2 * (MG_N * 16), MG_N * 16, 128);
+                        const uint32_t ahi = tmem_u + MG_COL_A + slot * 64 + kk * 8, alo = ahi + 32;
+                        tc5_mma_ts(d, alo, dh, MG_IDESC, (s | kk) > 0);
+                        tc5_mma_ts(d, ahi, dl, MG_IDESC, 1);
+                        tc5_mma_ts(d, ahi, dh, MG_IDESC, 1);
+                    }
+                    tc5_commit(&bar_empty[slot]);
+                    if (s == STAGES - 1) tc5_commit(&bar_dfull[db]);
+                }
+                __syncwarp();
             }
         }
     }
     tc5_fence_before();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == 8) {
         tc5_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(MG_TMEM_COLS) : "memory");
     }
@@ -280,12 +339,6 @@ extern "C" int mss_m2f_mask_logits(const float *mask_embed, const float *mask_fe
                                                                                   table + b0 * 2 * K * MG_N);
         MSS_CHECK_LAUNCH();
     }
-    static std::atomic<bool> attr_set{false};
-    if (!attr_set.load()) {
-        MSS_CHECK_CUDA(cudaFuncSetAttribute(mask_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)mask_gemm_smem(MG_MAX_K)));
-        attr_set.store(true);
-    }
     const int tiles_per_image = (int)((hw + 127) / 128);
     const int sms = sm_count();
     // B <= SMs: S = SMs / B slices per image, one work item per CTA; otherwise whole images, round-robin
@@ -293,8 +346,17 @@ extern "C" int mss_m2f_mask_logits(const float *mask_embed, const float *mask_fe
     if (slices < 1) slices = 1;
     const long long n_items = (long long)B * slices;
     const int grid = (int)std::min<long long>(n_items, (long long)sms);
-    mask_gemm_kernel<<<grid, MG_THREADS, mask_gemm_smem(K), st>>>(mask_features, (int)hw, K, Q, n_items, slices, tiles_per_image,
-                                                                 table, mask_logits);
+    const size_t smem = mask_gemm_smem(K);
+#define MG_LAUNCH(S)                                                                                                  \
+    case S:                                                                                                           \
+        MSS_CHECK_CUDA(cudaFuncSetAttribute(mask_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        mask_gemm_kernel<S><<<grid, MG_THREADS, smem, st>>>(mask_features, (int)hw, Q, n_items, slices, tiles_per_image, \
+                                                            table, mask_logits);                                      \
+        break;
+    switch (K / MG_STAGE_K) {
+        MG_LAUNCH(1) MG_LAUNCH(2) MG_LAUNCH(3) MG_LAUNCH(4) MG_LAUNCH(5) MG_LAUNCH(6) MG_LAUNCH(7) MG_LAUNCH(8)
+    }
+#undef MG_LAUNCH
     MSS_CHECK_LAUNCH();
     return MSS_OK;
 }
