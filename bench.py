@@ -323,6 +323,32 @@ def extra_head():
             "ms": ms, "head_mpix_s": px / ms / 1e3, "algorithmic_GBs": gbs, "frac_of_hbm_peak": gbs / peak}
 
 
+def extra_mask_gemm():
+    """Mask2Former mask-logit GEMM einsum("bqc,bchw->bqhw"), 8 x [100 x 256] x [256 x 256 x 512]."""
+    from multishiftseg_b200 import m2f
+    B, Q, K, h, w = 8, 100, 256, 256, 512
+    g = torch.Generator(device="cuda").manual_seed(7000)
+    feat = torch.randn((B, K, h, w), device="cuda", generator=g)
+    emb = torch.randn((B, Q, K), device="cuda", generator=g) / 16
+    for _ in range(3):
+        m2f.mask_logits(emb, feat)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        m2f.mask_logits(emb, feat)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    px = B * h * w
+    peak, _, _ = peaks()
+    gbs = px * (K * 4 + Q * 4) / ms / 1e6
+    return {"workload": "mask_embed x mask_features -> decoder-resolution mask logits, 8x[100x256]x[256x256x512] fp32 "
+                        "(tcgen05 3xTF32)",
+            "ms": ms, "us_per_image": ms * 1e3 / B, "algorithmic_GBs": gbs, "frac_of_hbm_peak": gbs / peak,
+            "fp32_equivalent_TFLOPs": 2.0 * px * Q * K / ms / 1e9}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -419,7 +445,7 @@ def main():
             del logits, out
             torch.cuda.empty_cache()
             line["extra"] = {"metrics": extra_metrics_stage(), "m2f": extra_m2f(), "confusion": extra_confusion(),
-                             "head": extra_head()}
+                             "head": extra_head(), "mask_gemm": extra_mask_gemm()}
         except Exception as e:   # side measurements must never take the headline down
             line["extra"] = {"error": repr(e)}
     if sampler is not None:
