@@ -235,14 +235,25 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
 }
 
 // 8-bit match for a tile without padding lanes: 4 instructions per bit (predicate, ballot, select, and)
+// Written in PTX so that one bit costs exactly predicate (and + setp -> one LOP3 with a predicate result), VOTE, SEL,
+// LOP3; the C form `bit = (d >> b) & 1; peers &= bit ? m : ~m` compiled to 6 instructions per bit (shift, and,
+// compare, select, vote, lop3) -- 48 of the pass's ~120 instructions per key (SASS, round 1).
+template <int B>
+__device__ __forceinline__ void match_bit(unsigned &peers, unsigned d) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t, m, x;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+        "selp.b32 x, 0, 0xffffffff, p;\n\t"
+        "lop3.b32 %0, %0, m, x, 0x60;\n\t}"                // peers & (m ^ x)
+        : "+r"(peers)
+        : "r"(d), "n"(1u << B));
+}
 __device__ __forceinline__ unsigned match8_full(unsigned d) {
     unsigned peers = 0xffffffffu;
-#pragma unroll
-    for (int b = 0; b < 8; b++) {
-        const bool bit = (d >> b) & 1u;
-        const unsigned m = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? m : ~m;
-    }
+    match_bit<0>(peers, d); match_bit<1>(peers, d); match_bit<2>(peers, d); match_bit<3>(peers, d);
+    match_bit<4>(peers, d); match_bit<5>(peers, d); match_bit<6>(peers, d); match_bit<7>(peers, d);
     return peers;
 }
 
