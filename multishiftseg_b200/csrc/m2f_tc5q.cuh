@@ -66,6 +66,11 @@ __device__ __forceinline__ void stg_stream_f2(float *p, float a, float b) {
 #ifndef TQ_RCP_FMA
 #define TQ_RCP_FMA 0     /* measured: 0 -> 145.1, 1 -> 148.2, 2 -> 147.2, 3 -> 151.5 us/image (issue slots co-limit) */
 #endif
+// TQ_RCP_PAIR: one MUFU.RCP for two sigmoids -- r = rcp(a0 * a1), 1/a0 = r * a1, 1/a1 = r * a0 (a = 1 + 2^e, e clamped
+// to 63 so the product stays finite) -- 1.5 instead of 2 MUFU per sigmoid at the price of 1.5 more FMA/ALU instructions.
+#ifndef TQ_RCP_PAIR
+#define TQ_RCP_PAIR 0     /* measured: 0 -> 143.6, 1 -> 143.3 us/image (neutral: the MUFU pipe is not alone on the critical path) */
+#endif
 #ifndef TQ_MMA_SLEEP_NS
 #define TQ_MMA_SLEEP_NS 32
 #endif
@@ -246,10 +251,28 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                             const float D = R - L, Ls = NL2E * L;
                             e[0] = fmaf(wxs0, D, Ls); e[1] = fmaf(wxs1, D, Ls); e[2] = fmaf(wxs2, D, Ls); e[3] = fmaf(wxs3, D, Ls);
                         }
+#if TQ_RCP_PAIR
+                        float sgp[4];
+                        if (j > 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; i += 2) {
+                                const float a0 = 1.0f + ex[i], a1 = 1.0f + ex[i + 1];
+                                float r;
+                                asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a0 * a1));
+                                sgp[i] = r * a1;
+                                sgp[i + 1] = r * a0;
+                            }
+                        }
+#endif
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
                             float sg = 0.f;
+#if TQ_RCP_PAIR
+                            if (j > 0) sg = sgp[i];
+                            if (false) {
+#else
                             if (j > 0) {
+#endif
 #if TQ_EXPERIMENT == 1 || TQ_EXPERIMENT == 4     /* timing experiment: no MUFU / no rcp */
                                 sg = fmaf(ex[i], 0.25f, 0.5f);
 #else
@@ -262,7 +285,7 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                                 ex[i] = e[i] * e[i];
 #else
                                 // (the FMA-pipe reciprocal needs a finite 1 + 2^e: clamp e, i.e. mask logits below -87)
-                                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex[i]) : "f"(i < TQ_RCP_FMA ? fminf(e[i], 126.f) : e[i]));
+                                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex[i]) : "f"(TQ_RCP_PAIR ? fminf(e[i], 63.f) : (i < TQ_RCP_FMA ? fminf(e[i], 126.f) : e[i])));
 #endif
                             }
                             if (j > 0) {
