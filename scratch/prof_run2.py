@@ -1,5 +1,5 @@
 """Short driver for ncu: one pass of each hot kernel at bench sizes (not a benchmark).
-argv[1]: which part to run (score|eval|m2f|all), argv[2]: eval images"""
+argv[1]: which part to run (score|eval|m2f|gemm|all), argv[2]: eval images"""
 import sys, torch
 sys.path.insert(0, ".")
 from multishiftseg_b200 import deeplab, m2f, metric
@@ -28,4 +28,15 @@ if what in ("m2f", "all"):
     for _ in range(2):
         m2f.anomaly_score_from_lowres(cls, lo, (H, W), (H, W))
         m2f.post_head_inference(cls, lo, (H, W), extra_channels=False)
+if what in ("gemm", "all"):
+    feat = torch.relu(torch.randn((8, 256, 512, 1024), device="cuda", generator=g))       # DeepLab head features
+    wc = torch.randn((19, 256), device="cuda", generator=g) / 16
+    wo = torch.randn((19, 256), device="cuda", generator=g) / 16
+    for _ in range(2):
+        deeplab.head_scores(feat, wc, wo)
+    del feat
+    mf = torch.randn((8, 256, 256, 512), device="cuda", generator=g)                      # Mask2Former mask features
+    emb = torch.randn((8, 100, 256), device="cuda", generator=g) / 16
+    for _ in range(2):
+        m2f.mask_logits(emb, mf)
 torch.cuda.synchronize()
