@@ -25,8 +25,8 @@ cap score deeplab_score score 1
 cap m2f 'm2f_tc5q' m2f 2
 cap sweep onesweep_pass eval 5
 cap hist radix_histogram eval 1
-cap head 'pixel_gemm_kernel.*HeadEpi' gemm 1
-cap maskgemm 'pixel_gemm_kernel.*MaskEpi' gemm 1
+cap head pixel_gemm_kernel gemm 1
+cap maskgemm pixel_gemm_kernel gemm 3
 python scratch/make_traffic.py $O/prof_${TAG}_score_raw.csv $TAG
 python scratch/ncu_summary.py raw $O/prof_${TAG}_*_raw.csv > $O/ncu_full_${TAG}_summary.txt 2>&1
 rm -f $O/prof_${TAG}_*.ncu-rep
