@@ -34,7 +34,8 @@ def check(feat, w_cls, w_ood, size=None):
     return dec1, score
 
 
-@pytest.mark.parametrize("B,K,h,w", [(1, 256, 16, 64), (2, 256, 37, 41), (1, 64, 8, 16), (3, 32, 5, 7), (1, 256, 128, 256)])
+@pytest.mark.parametrize("B,K,h,w", [(1, 256, 16, 64), (2, 256, 37, 41), (1, 64, 8, 16), (3, 32, 5, 7), (1, 256, 128, 256),
+                                     (2, 96, 9, 33), (1, 160, 20, 20), (1, 192, 3, 130), (2, 224, 17, 19), (150, 32, 4, 40)])
 def test_head_vs_torch_fp32(B, K, h, w):
     check(*make(B, K, h, w, seed=B * 1000 + K + h))
 

@@ -38,7 +38,8 @@ def check(embed, feat):
 
 
 @pytest.mark.parametrize("B,Q,K,h,w", [(1, 100, 256, 16, 64), (2, 100, 256, 37, 41), (1, 100, 64, 8, 16), (3, 7, 32, 5, 7),
-                                       (1, 112, 256, 24, 40), (1, 100, 256, 128, 256)])
+                                       (1, 112, 256, 24, 40), (1, 100, 256, 128, 256), (2, 1, 96, 6, 50), (1, 100, 160, 19, 23),
+                                       (1, 57, 192, 16, 16), (2, 100, 224, 11, 40)])
 def test_mask_logits_vs_torch_fp32(B, Q, K, h, w):
     check(*make(B, Q, K, h, w, seed=B * 1000 + K + h))
 
