@@ -315,7 +315,8 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
     }
     // phase 2 (serial per warp; item order == memory order, hence stable): running per-digit counters.
     // rank[i] bit 15 carries the label so it needs no register of its own.
-    unsigned short rank[SORT_IPT];
+    // two 16-bit ranks per register (8 registers, not 16: the kernel has to fit 64 registers for 4 CTAs per SM)
+    unsigned rank2[SORT_IPT / 2];
     const unsigned lt = lanemask_lt();
     unsigned *wh = sm.warp_hist[warp];
 #pragma unroll
@@ -329,7 +330,8 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
             wh[d] = old + __popc(peers[i]);
         }
         old = __shfl_sync(0xffffffffu, old, __ffs(peers[i]) - 1);
-        rank[i] = (unsigned short)((old + below) | ((unsigned)sm.vals[wbase + i * 32] << 15));
+        const unsigned r16 = (old + below) | ((unsigned)sm.vals[wbase + i * 32] << 15);
+        rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r16 << 16)) : r16;
         __syncwarp();
     }
     __syncthreads();
@@ -370,9 +372,10 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
         if (FULL || wbase + i * 32 < tile_n) {
-            const unsigned pos = wh[digit_of(key[i])] + (rank[i] & 0x7fffu);
+            const unsigned r16 = (i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
+            const unsigned pos = wh[digit_of(key[i])] + (r16 & 0x7fffu);
             sm.keys[pos] = key[i];
-            sm.vals[pos] = (uint8_t)(rank[i] >> 15);
+            sm.vals[pos] = (uint8_t)(r16 >> 15);
         }
     }
 
@@ -437,8 +440,11 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
     }
 }
 
+#ifndef SORT_CTAS_PER_SM
+#define SORT_CTAS_PER_SM 4
+#endif
 template <typename DigitFn, bool MULTI = false>
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+__global__ void __launch_bounds__(SORT_THREADS, SORT_CTAS_PER_SM)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out,
                      const uint8_t *__restrict__ vals_in, uint8_t *__restrict__ vals_out, long long n,
                      const unsigned long long *__restrict__ bin_base, unsigned long long *tile_status,
