@@ -23,7 +23,7 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int LB_WINDOW = 8;                        // look-back statuses fetched per round trip
+constexpr int LB_WINDOW = 8;                        // look-back statuses fetched per round trip (16: 39.7 vs 40.8 Gpairs/s)
 
 struct ShiftDigit {
     int shift;
