@@ -349,6 +349,30 @@ def extra_mask_gemm():
             "fp32_equivalent_TFLOPs": 2.0 * px * Q * K / ms / 1e9}
 
 
+def extra_backward():
+    """backward of energy_func (train_deeplab.py:197-198 differentiates through the scoring path)."""
+    from multishiftseg_b200 import deeplab
+    g = torch.Generator(device="cuda").manual_seed(8000)
+    x = torch.randn((B_PER_GPU, C, H, W), device="cuda", generator=g).requires_grad_(True)
+    go = torch.randn((B_PER_GPU, H, W), device="cuda", generator=g)
+    s = deeplab.energy_func(x)
+    for _ in range(3):
+        torch.autograd.grad(s, x, go, retain_graph=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        torch.autograd.grad(s, x, go, retain_graph=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    px = B_PER_GPU * H * W
+    peak, _, _ = peaks()
+    gbs = px * (2 * C * 4 + 4) / ms / 1e6
+    return {"workload": "energy_func backward (-softmax * grad), 16x19x1024x2048 fp32 logits", "ms": ms,
+            "mpix_s": px / ms / 1e3, "algorithmic_GBs": gbs, "frac_of_hbm_peak": gbs / peak}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -445,7 +469,7 @@ def main():
             del logits, out
             torch.cuda.empty_cache()
             line["extra"] = {"metrics": extra_metrics_stage(), "m2f": extra_m2f(), "confusion": extra_confusion(),
-                             "head": extra_head(), "mask_gemm": extra_mask_gemm()}
+                             "head": extra_head(), "mask_gemm": extra_mask_gemm(), "backward": extra_backward()}
         except Exception as e:   # side measurements must never take the headline down
             line["extra"] = {"error": repr(e)}
     if sampler is not None:

@@ -108,6 +108,19 @@ MSS_API int mss_upsample_bilinear(const float *in, int64_t NC, int h, int w, flo
 MSS_API int mss_deeplab_anomaly_score(const float *ood_logits, int64_t B, int C, int h, int w,
                               float *scratch, float *score, int H, int W, void *stream);
 
+/* (DeepLab half) backward of the scoring ops, for the trainer's use of the same path with autograd
+ * (train_deeplab.py:197-198: the loss of lib/loss.py:34-147 is a function of the anomaly-score map):
+ *   mss_deeplab_energy_backward          grad_logits[b,c,p] = -softmax(logits[b,:,p])_c * grad_score[b,p]   (deepv3.py:251-253)
+ *   mss_upsample_bilinear_backward       grad_in = A^T grad_out, A = the tap matrix of mss_upsample_bilinear (mynn.py:28-33)
+ *   mss_deeplab_anomaly_score_backward   both fused (deepv3.py:283): grad_score [B,H,W] -> grad of ood_logits [B,C,h,w]
+ * Gather form, no atomics: deterministic. */
+MSS_API int mss_deeplab_energy_backward(const float *logits, const float *grad_score, int64_t B, int C, int64_t HW,
+                                float *grad_logits, void *stream);
+MSS_API int mss_upsample_bilinear_backward(const float *grad_out, int64_t NC, int h, int w, float *grad_in, int H, int W,
+                                   int align_corners, void *stream);
+MSS_API int mss_deeplab_anomaly_score_backward(const float *ood_logits, const float *grad_score, int64_t B, int C, int h,
+                                       int w, int H, int W, float *grad_logits, void *stream);
+
 /*  DeepLabv3+ head fusion, deepv3.py:279-283: the two bias-free 1x1 convolutions on the decoder
  * feature map and the energy score in one pass (tcgen05 3xTF32 GEMM, feature read once):
  *   feature [B, K, hw] NCHW fp32;  w_cls = final[-1].weight, w_ood = ood_head.weight, each [C, K] row-major

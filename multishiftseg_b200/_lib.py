@@ -55,6 +55,9 @@ SIGNATURES = {
     "mss_deeplab_score": (_i, [_p, _i64, _i, _i64, _u, _p, _p, _p, _p, _p, _i, _i64, _i64, _u, _EV, _p]),
     "mss_upsample_bilinear": (_i, [_p, _i64, _i, _i, _p, _i, _i, _i, _p]),
     "mss_deeplab_anomaly_score": (_i, [_p, _i64, _i, _i, _i, _p, _p, _i, _i, _p]),
+    "mss_deeplab_energy_backward": (_i, [_p, _p, _i64, _i, _i64, _p, _p]),
+    "mss_upsample_bilinear_backward": (_i, [_p, _i64, _i, _i, _p, _i, _i, _i, _p]),
+    "mss_deeplab_anomaly_score_backward": (_i, [_p, _p, _i64, _i, _i, _i, _i, _i, _p, _p]),
     "mss_deeplab_head_workspace_bytes": (_sz, [_i]),
     "mss_deeplab_head": (_i, [_p, _i64, _i, _i64, _p, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "mss_m2f_workspace_bytes": (_sz, [_i64, _i, _i]),

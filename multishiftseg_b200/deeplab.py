@@ -71,20 +71,101 @@ def score_maps(logit: torch.Tensor, which: Iterable[str] = ("energy",), *, label
     return out
 
 
+def _wants_grad(*ts: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
+
+class _EnergyFn(torch.autograd.Function):
+    """energy_func with its backward (train_deeplab.py:197-198 differentiates through it)."""
+
+    @staticmethod
+    def forward(ctx, logit):
+        x = _prep_logits(logit)
+        ctx.save_for_backward(x)
+        ctx.in_dtype = logit.dtype
+        return score_maps(x, ("energy",))["energy"]
+
+    @staticmethod
+    def backward(ctx, grad):
+        (x,) = ctx.saved_tensors
+        g = grad.float().contiguous()
+        B, Cn = x.shape[0], x.shape[1]
+        HW = x.numel() // max(B * Cn, 1)
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = L.load().mss_deeplab_energy_backward(x.data_ptr(), g.data_ptr(), B, Cn, HW, gx.data_ptr(),
+                                                      L.stream_ptr(x.device))
+        L.check(rc, "mss_deeplab_energy_backward")
+        return gx.to(ctx.in_dtype)
+
+
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W, align_corners):
+        ctx.shape, ctx.align, ctx.in_dtype = tuple(x.shape), bool(align_corners), x.dtype
+        return _upsample_forward(x, H, W, align_corners)
+
+    @staticmethod
+    def backward(ctx, grad):
+        N, Cn, h, w = ctx.shape
+        g = grad.float().contiguous()
+        H, W = g.shape[-2:]
+        gx = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            rc = L.load().mss_upsample_bilinear_backward(g.data_ptr(), N * Cn, h, w, gx.data_ptr(), H, W,
+                                                         1 if ctx.align else 0, L.stream_ptr(g.device))
+        L.check(rc, "mss_upsample_bilinear_backward")
+        return gx.to(ctx.in_dtype), None, None, None
+
+
+class _AnomalyScoreFn(torch.autograd.Function):
+    """deepv3.py:283 with a fused backward: the upsampled gradient is gathered per head-resolution pixel and
+    turned into -softmax(dec2) * g in one kernel."""
+
+    @staticmethod
+    def forward(ctx, ood_logit, H, W):
+        x = _prep_logits(ood_logit)
+        ctx.save_for_backward(x)
+        ctx.size, ctx.in_dtype = (H, W), ood_logit.dtype
+        return _anomaly_score_forward(x, H, W)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (x,) = ctx.saved_tensors
+        B, Cn, h, w = x.shape
+        H, W = ctx.size
+        g = grad.float().contiguous()
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = L.load().mss_deeplab_anomaly_score_backward(x.data_ptr(), g.data_ptr(), B, Cn, h, w, H, W, gx.data_ptr(),
+                                                             L.stream_ptr(x.device))
+        L.check(rc, "mss_deeplab_anomaly_score_backward")
+        return gx.to(ctx.in_dtype), None, None
+
+
 def energy_func(logit: torch.Tensor) -> torch.Tensor:
     """``-(1. * torch.logsumexp(logit, dim=1))`` -- deepv3.py:251-253 (call as a function, or bind it
-    as the model's method: ``DeepWV3Plus.energy_func = lambda self, x: energy_func(x)``)."""
+    as the model's method: ``DeepWV3Plus.energy_func = lambda self, x: energy_func(x)``).  Differentiable: with
+    autograd enabled and ``logit.requires_grad`` the backward (``-softmax(logit) * grad``) runs as a CUDA kernel."""
+    if _wants_grad(logit):
+        return _EnergyFn.apply(logit)
     return score_maps(logit, ("energy",))["energy"]
 
 
 def Upsample(x: torch.Tensor, size: Sequence[int], align_corners: bool = True) -> torch.Tensor:
-    """mynn.py:28-33: ``F.interpolate(x, size=size, mode='bilinear', align_corners=True)`` for [N,C,h,w]."""
+    """mynn.py:28-33: ``F.interpolate(x, size=size, mode='bilinear', align_corners=True)`` for [N,C,h,w]
+    (differentiable: the backward is the exact adjoint of the forward's taps, gather form, deterministic)."""
     L.require_cuda(x, "x")
     if x.dim() != 4:
         raise ValueError("Upsample expects [N, C, h, w]")
+    if _wants_grad(x):
+        return _UpsampleFn.apply(x, int(size[0]), int(size[1]), align_corners)
+    return _upsample_forward(x, int(size[0]), int(size[1]), align_corners)
+
+
+def _upsample_forward(x: torch.Tensor, H: int, W: int, align_corners: bool) -> torch.Tensor:
     x = x.float().contiguous() if x.dtype != torch.float32 else x.contiguous()
     N, Cn, h, w = x.shape
-    H, W = int(size[0]), int(size[1])
     out = torch.empty((N, Cn, H, W), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         rc = L.load().mss_upsample_bilinear(x.data_ptr(), N * Cn, h, w, out.data_ptr(), H, W,
@@ -94,12 +175,17 @@ def Upsample(x: torch.Tensor, size: Sequence[int], align_corners: bool = True) -
 
 
 def anomaly_score(ood_logit: torch.Tensor, size: Sequence[int]) -> torch.Tensor:
-    """deepv3.py:283: ``Upsample(self.energy_func(dec2).unsqueeze(1), x_size[2:]).squeeze(1)``."""
-    ood_logit = _prep_logits(ood_logit)
+    """deepv3.py:283: ``Upsample(self.energy_func(dec2).unsqueeze(1), x_size[2:]).squeeze(1)`` (differentiable)."""
     if ood_logit.dim() != 4:
         raise ValueError("ood_logit must be [B, C, h, w]")
+    if _wants_grad(ood_logit):
+        L.require_cuda(ood_logit, "logit")
+        return _AnomalyScoreFn.apply(ood_logit, int(size[0]), int(size[1]))
+    return _anomaly_score_forward(_prep_logits(ood_logit), int(size[0]), int(size[1]))
+
+
+def _anomaly_score_forward(ood_logit: torch.Tensor, H: int, W: int) -> torch.Tensor:
     B, Cn, h, w = ood_logit.shape
-    H, W = int(size[0]), int(size[1])
     scratch = torch.empty((B, h, w), dtype=torch.float32, device=ood_logit.device)
     out = torch.empty((B, H, W), dtype=torch.float32, device=ood_logit.device)
     with torch.cuda.device(ood_logit.device):
