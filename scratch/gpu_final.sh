@@ -10,6 +10,7 @@ timeout 300 python scratch/bench_sort.py > $O/sort_$TAG.log 2>&1; cat $O/sort_$T
 timeout 300 python scratch/bench_m2f.py 0 8 4 2 > $O/m2f_$TAG.log 2>&1; cat $O/m2f_$TAG.log
 timeout 200 python scratch/bench_maskgemm.py > $O/maskgemm_$TAG.log 2>&1; cat $O/maskgemm_$TAG.log
 timeout 200 python scratch/bench_head.py > $O/head_$TAG.log 2>&1; cat $O/head_$TAG.log
+timeout 200 python scratch/bench_backward.py > $O/backward_$TAG.log 2>&1; cat $O/backward_$TAG.log
 timeout 600 python bench_sweep.py > $O/sweep_$TAG.json 2> $O/sweep_$TAG.err; cat $O/sweep_$TAG.json
 timeout 600 python bench_sweep.py --cfg 5 > $O/sweep5_$TAG.json 2> $O/sweep5_$TAG.err; cat $O/sweep5_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench_$TAG.csv python bench.py --steps 3 --warmup 3 --no-cpu > $O/ncu_bench_$TAG.log 2>&1
