@@ -52,6 +52,16 @@ deeplab_score_vec4_kernel(const float *__restrict__ logits, long long HW, long l
         const bool active = v < n_vec;
         float sc[4] = {0.f, 0.f, 0.f, 0.f};
         long long pix = 0;
+        unsigned mask = 0;
+        AppendTicket ticket;
+        if (EMIT) {
+            // labels first: the CTA's range in the evaluator is reserved (one atomic) while the logits are scored
+            if (active) {
+                const long long b = v / HW4, p4 = v - b * HW4;
+                mask = classify4(labels, label_dtype, b * HW + (p4 << 2), 4, id_in, id_out, true);
+            }
+            ticket = block_reserve4<256>(mask, ev);
+        }
         if (active) {
             const long long b = v / HW4, p4 = v - b * HW4;
             const float *base = logits + (b * C) * HW + (p4 << 2);
@@ -97,10 +107,7 @@ deeplab_score_vec4_kernel(const float *__restrict__ logits, long long HW, long l
                 sc[0] = k.x; sc[1] = k.y; sc[2] = k.z; sc[3] = k.w;
             }
         }
-        if (EMIT) {
-            unsigned mask = active ? classify4(labels, label_dtype, pix, 4, id_in, id_out, true) : 0u;
-            block_append4<256>(sc, mask, ev);
-        }
+        if (EMIT) block_commit4<256>(sc, mask, ticket, ev);
     }
 }
 
