@@ -75,6 +75,26 @@ def test_missing_cuda_raises_instead_of_falling_back():
         metric.eval_ood_measure(np.zeros(4, np.float32), np.array([0, 1, 0, 1]))
     with pytest.raises(_lib.MssError):
         deeplab.energy_func(torch.zeros(1, 19, 4, 4))
+    # every entry point of the Python mirror refuses CPU tensors (no silent PyTorch fallback), with or without autograd
+    from multishiftseg_b200 import m2f, segmetric
+    x = torch.zeros(1, 19, 4, 4)
+    calls = [
+        lambda: deeplab.energy_func(x.clone().requires_grad_(True)),
+        lambda: deeplab.anomaly_score(x, (8, 8)),
+        lambda: deeplab.anomaly_score(x.clone().requires_grad_(True), (8, 8)),
+        lambda: deeplab.Upsample(x, (8, 8)),
+        lambda: deeplab.score_maps(x, ("energy", "entropy")),
+        lambda: deeplab.head_scores(torch.zeros(1, 32, 4, 4), torch.zeros(19, 32), torch.zeros(19, 32)),
+        lambda: m2f.mask_logits(torch.zeros(1, 100, 32), torch.zeros(1, 32, 4, 4)),
+        lambda: m2f.anomaly_score_from_lowres(torch.zeros(1, 100, 20), torch.zeros(1, 100, 4, 4), (16, 16), (16, 16)),
+        lambda: m2f.anomaly_score_from_features(torch.zeros(1, 100, 20), torch.zeros(1, 100, 32), torch.zeros(1, 32, 4, 4),
+                                                (16, 16), (16, 16)),
+        lambda: m2f.semantic_inference(torch.zeros(100, 20), torch.zeros(100, 8, 8)),
+        lambda: segmetric.ConfusionAccumulator(19),
+    ]
+    for i, call in enumerate(calls):
+        with pytest.raises(_lib.MssError):
+            call()
 
 
 @pytest.mark.parametrize("n", [1, 7, 8, 128, 129, 1000, 4097, 100_003, 1_000_001, 12_345_678])
