@@ -146,7 +146,7 @@ void oracle_metrics_from_counts(const int64_t *tps, const int64_t *fps, int64_t 
     const double P = (double)tps[T - 1], N = (double)fps[T - 1];
 
     /* AUROC: drop collinear points, prepend the origin, trapezoid */
-    double *terms = malloc(sizeof(double) * (T > 0 ? T : 1));
+    double *terms = calloc((size_t)(T > 0 ? T : 1), sizeof(double));
     int64_t nt = 0;
     double pf = 0.0 / N, pt = 0.0 / P;     /* the prepended (0, 0) point */
     for (int64_t k = 0; k < T; k++) {
