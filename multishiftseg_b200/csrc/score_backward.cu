@@ -37,26 +37,47 @@ __device__ __forceinline__ void bw_out_range(int i, float scale, int align, int 
     hi = min(out_size - 1, (int)ceilf(((float)i + 1.f + off) * inv - off) + 1);
 }
 
-// sum over the output pixels (Y, X) of plane `g` whose forward taps include input pixel (y, x)
+// weight with which output index `dst` reads input index `i` in the forward (0 if it does not)
+__device__ __forceinline__ float bw_tap_weight(int dst, int i, float scale, int align, int in_size) {
+    int a0, a1;
+    float l0, l1;
+    bw_src_index(dst, scale, align, in_size, a0, a1, l0, l1);
+    return (a0 == i ? l0 : 0.f) + (a1 == i ? l1 : 0.f);
+}
+
+// sum over the output pixels (Y, X) of plane `g` whose forward taps include input pixel (y, x).  The column weights
+// are computed once per thread (registers, ranges of up to BW_R candidates -- any upsampling factor up to ~2.5) instead
+// of once per candidate row; the order of the additions is the same in both forms.
+constexpr int BW_R = 8;
 __device__ __forceinline__ float bw_gather(const float *__restrict__ g, int y, int x, int h, int w, int H, int W, float sh,
                                            float sw, int align) {
     int Y0, Y1, X0, X1;
     bw_out_range(y, sh, align, H, Y0, Y1);
     bw_out_range(x, sw, align, W, X0, X1);
     float acc = 0.f;
+    if (X1 - X0 < BW_R) {
+        float wxv[BW_R];
+#pragma unroll
+        for (int k = 0; k < BW_R; k++) wxv[k] = (X0 + k <= X1) ? bw_tap_weight(X0 + k, x, sw, align, w) : 0.f;
+        for (int Y = Y0; Y <= Y1; Y++) {
+            const float wy = bw_tap_weight(Y, y, sh, align, h);
+            if (wy == 0.f) continue;
+            const float *row = g + (long long)Y * W + X0;
+            float racc = 0.f;
+#pragma unroll
+            for (int k = 0; k < BW_R; k++)
+                if (wxv[k] != 0.f) racc += wxv[k] * __ldg(row + k);
+            acc += wy * racc;
+        }
+        return acc;
+    }
     for (int Y = Y0; Y <= Y1; Y++) {
-        int a0, a1;
-        float l0, l1;
-        bw_src_index(Y, sh, align, h, a0, a1, l0, l1);
-        const float wy = (a0 == y ? l0 : 0.f) + (a1 == y ? l1 : 0.f);
+        const float wy = bw_tap_weight(Y, y, sh, align, h);
         if (wy == 0.f) continue;
         const float *row = g + (long long)Y * W;
         float racc = 0.f;
         for (int X = X0; X <= X1; X++) {
-            int b0, b1;
-            float m0, m1;
-            bw_src_index(X, sw, align, w, b0, b1, m0, m1);
-            const float wx = (b0 == x ? m0 : 0.f) + (b1 == x ? m1 : 0.f);
+            const float wx = bw_tap_weight(X, x, sw, align, w);
             if (wx != 0.f) racc += wx * __ldg(row + X);
         }
         acc += wy * racc;
