@@ -14,8 +14,13 @@ rank scores its own 16-image batch.  Prints ONE JSON line (rank 0).
              host score maps out; H2D + D2H inside the timed region)
   roofline   achieved HBM GB/s of the scoring kernel vs MEASURED_PEAKS.json
   cpu_baseline  the oracle port (torch-CPU one-liners of deepv3.py:251-253 + extras) on the host cores
-  extra      the other two kernels of the path (exact metrics, Mask2Former fused inference), each with
-             its own throughput / roofline fraction, so one run documents the whole path
+  extra.eval_sweep   (every N) BASELINE configs[3]: the 2000-image evaluation sweep -- fused scoring + append, ONE exact
+             global metric through the key-range exchange -- with eval images/s, per-phase ms, the float64 results
+             as hex and `bit_exact_vs_pool` (sweep == the pool on one GPU == the CPU oracle), so the driver's
+             N = 1, 2, 4, 8 lines carry the real multi-GPU path and its strong scaling
+  extra      (N = 1) the other kernels of the path (exact metrics with a CUB yardstick, Mask2Former fused inference,
+             head GEMMs, ...), each with its own throughput / roofline fraction, and the CPU legs of BASELINE.md
+             section 3 (cfg-1, cfg-3, cfg-4 subset) with GPU == CPU metric equality checked in the run
 
 `--impl reference` times the reference's own CPU implementation of the path (oracle port: the reference is
 plain PyTorch / numpy / scikit-learn, which is exactly what the port calls) on this box's host cores.
@@ -40,6 +45,13 @@ WHICH = ("maxlogit", "energy", "entropy")
 BYTES_PER_PX = 4 * C + 4 * len(WHICH)           # 88: SURVEY 8(d)
 METRIC = "Mpix/s scored (DeepLabv3+ max-logit+energy+entropy, 16x19x1024x2048 fp32 per GPU)"
 WORKLOAD = "cfg2: DeepLabv3+ scoring batch 16x19x1024x2048 fp32 -> max-logit + energy + entropy"
+
+
+def common_config(world):
+    """identical for the b200 and the reference arm (the driver compares them)"""
+    return {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "classes": C, "frame": [H, W],
+            "l2": "input 2.55 GB per step >> 126 MB L2, no flush needed",
+            "parallelism": f"images sharded over {world} GPU(s), no data-path collective"}
 
 
 def peaks():
@@ -159,34 +171,39 @@ def cpu_reference_scoring(sample_images, min_seconds=10.0, max_seconds=40.0):
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU path (oracle port) for the same metric / config."""
+    """`--impl reference`: the reference's own CPU path (oracle port) for the same metric / config: every step scores
+    the whole 16-image batch (in 2-image slices, to bound the fp32 temporaries of the eager expressions)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import scoring_oracle as so
     torch.set_num_threads(os.cpu_count() or 1)
-    sample = 2                                   # images per step (of the 16-image batch): bounded sample
     g = torch.Generator().manual_seed(0)
-    x = torch.randn((sample, C, H, W), generator=g)
+    x = torch.randn((B_PER_GPU, C, H, W), generator=g)
 
     def step():
-        return so.maxlogit_score(x), so.energy_func(x), so.entropy_score(x)
+        out = []
+        for b in range(0, B_PER_GPU, 2):
+            xs = x[b:b + 2]
+            out.append((so.maxlogit_score(xs), so.energy_func(xs), so.entropy_score(xs)))
+        return out
 
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     el = time.perf_counter() - t0
-    mpix = args.steps * sample * H * W / el / 1e6
+    mpix = args.steps * B_PER_GPU * H * W / el / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} of 16 images per step, CPU"},
+        "config": common_config(args.gpus),
         "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{args.steps} steps x {sample} images (1024x2048) of the 16-image batch, "
-                                   "torch-CPU restatement of deepv3.py:251-253 + max-logit + entropy"},
+                         "sample": f"{args.steps} steps x the whole 16-image batch (1024x2048), torch-CPU restatement of "
+                                   "deepv3.py:251-253 + max-logit + entropy (oracle/scoring_oracle.py); host threads only, "
+                                   "one batch whatever --gpus says"},
         "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,15 +212,39 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------------------
 def extra_metrics_stage(images=4):
-    """Exact AUROC/AP/FPR95 on `images` x 1024 x 2048 score/label maps resident in HBM."""
+    """Exact AUROC/AP/FPR95 on `images` x 1024 x 2048 score/label maps resident in HBM, the sort alone at three sizes
+    beside cub::DeviceRadixSort on the same box, and the one-image latency."""
     from multishiftseg_b200 import metric
-    n = images * H * W
+    peak, _, _ = peaks()
     g = torch.Generator(device="cuda").manual_seed(4000)
-    lab = torch.zeros(n, dtype=torch.uint8, device="cuda")
-    r = torch.rand(n, device="cuda", generator=g)
-    lab[r < 0.05] = 1
-    lab[r > 0.95] = 255
-    s = torch.randn(n, device="cuda", generator=g) + (lab == 1) * 1.5
+
+    def case(n):
+        lab = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        r = torch.rand(n, device="cuda", generator=g)
+        lab[r < 0.05] = 1
+        lab[r > 0.95] = 255
+        s = torch.randn(n, device="cuda", generator=g) + (lab == 1) * 1.5
+        return s, lab
+
+    def sort_ms(s, lab):
+        buf = metric.PairBuffer(s.numel(), "cuda")
+        buf.append(s, lab)
+        m = buf.read_state()[0]
+        keys0 = buf.keys.clone()
+        ts = []
+        for _ in range(6):
+            buf.keys.copy_(keys0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            buf.sort(m)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts[1:]), m
+
+    n = images * H * W
+    s, lab = case(n)
     for _ in range(2):
         res = metric.eval_ood_measure(s, lab)
     torch.cuda.synchronize()
@@ -214,31 +255,36 @@ def extra_metrics_stage(images=4):
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
     t = statistics.median(ts)
-    # isolate the sort (dominant kernel family): pairs already built
-    buf = metric.PairBuffer(n, "cuda")
-    buf.append(s, lab)
-    m = buf.read_state()[0]
-    keys0, labs0 = buf.keys.clone(), buf.labs.clone()
-    sort_ms = []
-    for _ in range(5):
-        buf.keys.copy_(keys0)
-        buf.labs.copy_(labs0)
+    sm, m = sort_ms(s, lab)
+    out = {"workload": f"exact AUROC/AP/FPR95, {images}x1024x2048 px in HBM (90/5/5 % ID/OOD/ignore, continuous scores: T ~= N)",
+           "mpix_s": n / t / 1e6, "images_s": images / t, "ms": t * 1e3, "valid_keys": m,
+           "result": [float(x) for x in res],
+           "sort": {"ms": sm, "gkeys_s": m / sm / 1e6,
+                    "algorithmic_GBs": m * 4 / sm / 1e6,       # 4 B/key read once (the label is the stream, not a byte)
+                    "implementation_GBs": m * 36 / sm / 1e6,   # 4 + 4 x (4 + 4) B/key actually moved
+                    "frac_of_hbm_peak_impl": m * 36 / sm / 1e6 / peak}}
+    del s, lab
+    # one image (what test_deeplab.py evaluates per small dataset) and the larger sizes
+    sizes = [H * W, 16 * H * W, 64 * H * W]
+    rows = []
+    for nn in sizes:
+        s, lab = case(nn)
+        metric.eval_ood_measure(s, lab)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        metric.sort_pairs(buf.keys, buf.labs, m)
-        e1.record()
-        torch.cuda.synchronize()
-        sort_ms.append(e0.elapsed_time(e1))
-    sm = statistics.median(sort_ms)
-    peak, _, _ = peaks()
-    return {"workload": f"exact AUROC/AP/FPR95, {images}x1024x2048 px in HBM (90/5/5 % ID/OOD/ignore)",
-            "mpix_s": n / t / 1e6, "images_s": images / t, "ms": t * 1e3, "valid_pairs": m,
-            "result": [float(x) for x in res],
-            "sort": {"ms": sm, "gkeys_s": m / sm / 1e6,
-                     "algorithmic_GBs": m * 5 / sm / 1e6,       # 5 B/pair read once (SURVEY 8d lower bound)
-                     "implementation_GBs": m * 44 / sm / 1e6,   # 4 + 4 x (5 + 5) B/pair actually moved
-                     "frac_of_hbm_peak_impl": m * 44 / sm / 1e6 / peak}}
+        tt = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            metric.eval_ood_measure(s, lab)
+            torch.cuda.synchronize()
+            tt.append(time.perf_counter() - t0)
+        sm2, m2 = sort_ms(s, lab)
+        rows.append({"px": nn, "eval_ood_measure_ms": statistics.median(tt) * 1e3, "gpix_s": nn / statistics.median(tt) / 1e9,
+                     "valid_keys": m2, "sort_ms": sm2, "sort_gkeys_s": m2 / sm2 / 1e6})
+        del s, lab
+    out["by_size"] = rows
+    torch.cuda.empty_cache()
+    out["sort"]["cub_yardstick"] = cub_yardstick([2 * H * W, 4 * H * W, 16 * H * W, 64 * H * W])
+    return out
 
 
 def extra_m2f(batch=8):
@@ -389,6 +435,132 @@ def extra_backward():
             "mpix_s": px / ms / 1e3, "algorithmic_GBs": gbs, "frac_of_hbm_peak": gbs / peak}
 
 
+def _best_of(fn, reps=3):
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = fn()
+        ts.append(time.perf_counter() - t0)
+    return min(ts), r
+
+
+def _gpu_ms(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    return statistics.median(ts), r
+
+
+def cpu_legs():
+    """the reference's CPU path (oracle port: the same torch / numpy / scikit-learn calls) timed on
+    this box's host cores beside the GPU path, and the metric triples compared for EQUALITY in the run."""
+    import numpy as np
+    import bench_sweep
+    from multishiftseg_b200 import deeplab, m2f, metric
+    from oracle import metrics_oracle as mo, scoring_oracle as so
+    hexes = lambda r: None if r is None else [float(v).hex() for v in r]
+    out = {"cores": os.cpu_count(), "torch_threads": torch.get_num_threads(),
+           "note": "CPU = oracle port of the reference flow (torch-CPU scoring with all threads; numpy + scikit-learn "
+                   "metrics, single-threaded as in the reference); wall clock, best of 3 where repeated"}
+    px = H * W
+    # ---- cfg-1: one image, energy + AUROC/AP/FPR95 (SURVEY 8d synthetic input) ---------------------------------
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((1, C, H, W), generator=g)
+    r = torch.rand((1, H, W), generator=g)
+    lab = torch.where(r < 0.05, 1, torch.where(r > 0.95, 255, 0)).to(torch.int64)
+    x = torch.where((lab == 1).unsqueeze(1), 0.5 * x, 2.0 * x)
+    t_score, e_cpu = _best_of(lambda: so.energy_func(x))
+    conf, labn = e_cpu.numpy(), lab.numpy()                        # float32 / int64, as test_deeplab.py:98-101 passes them
+    t_metric, ref = _best_of(lambda: mo.eval_ood_measure(conf, labn), reps=1)
+    xg, lg = x.cuda(), lab.cuda()
+    g_score_ms, e_gpu = _gpu_ms(lambda: deeplab.energy_func(xg))
+    g_metric_ms, got_dev = _gpu_ms(lambda: metric.eval_ood_measure(e_gpu, lg))
+    # the call the reference makes: numpy float32 scores + numpy int64 labels on the HOST, result back on the host
+    g_e2e_ms, got_host = _gpu_ms(lambda: metric.eval_ood_measure(conf, labn))
+    out["cfg1"] = {
+        "workload": "cfg1: 1x19x1024x2048 logits -> energy -> exact AUROC/AP/FPR95 (90/5/5 % ID/OOD/ignore)",
+        "cpu": {"score_s": t_score, "score_mpix_s": px / t_score / 1e6, "metric_s": t_metric,
+                "metric_mpix_s": px / t_metric / 1e6, "result_hex": hexes(ref)},
+        "gpu": {"score_ms": g_score_ms, "score_mpix_s": px / g_score_ms / 1e3, "metric_ms_device_inputs": g_metric_ms,
+                "metric_mpix_s_device_inputs": px / g_metric_ms / 1e3,
+                "metric_e2e_ms_host_numpy_inputs": g_e2e_ms, "metric_e2e_mpix_s": px / g_e2e_ms / 1e3,
+                "metric_e2e_h2d_bytes": conf.nbytes + labn.nbytes, "metric_e2e_d2h_bytes": 24,
+                "result_hex_same_score_map": hexes(got_host), "result_hex_gpu_score_map": hexes(got_dev)},
+        "metric_equal_given_equal_score_maps": hexes(got_host) == hexes(ref),
+        "score_max_rel_err": float(((e_gpu.cpu() - e_cpu).abs() / e_cpu.abs().clamp_min(1e-6)).max()),
+        "metric_stage_speedup_e2e": t_metric * 1e3 / g_e2e_ms,
+    }
+    del xg, lg, e_gpu
+    # ---- cfg-3: Mask2Former post-head inference, one image ------------------------------------------------------
+    g = torch.Generator().manual_seed(3000)
+    cls = 3.0 * torch.randn((1, 100, 20), generator=g)
+    lo = 4.0 * torch.randn((1, 100, 256, 512), generator=g)
+    t_m2f, a_cpu = _best_of(lambda: so.m2f_anomaly_from_lowres(cls, lo, (H, W), (H, W)), reps=2)
+    clsg, log_ = cls.cuda(), lo.cuda()
+    g_m2f_ms, a_gpu = _gpu_ms(lambda: m2f.anomaly_score_from_lowres(clsg, log_, (H, W), (H, W)))
+    out["cfg3"] = {
+        "workload": "cfg3 (one image of the batch): Q=100, C=19+1, masks 256x512 -> 1024x2048, 1 - max_c score",
+        "cpu": {"s_per_image": t_m2f, "mpix_s": px / t_m2f / 1e6},
+        "gpu": {"ms_per_image_batch1": g_m2f_ms, "mpix_s": px / g_m2f_ms / 1e3},
+        "allclose_rtol1e-5_atol2e-6": bool(torch.allclose(a_gpu.cpu(), a_cpu, rtol=1e-5, atol=2e-6)),
+    }
+    del clsg, log_, a_gpu
+    # ---- cfg-4 / cfg-5 metric stage on a SUBSET: 8 images of the sweep's pool (the full 2000 images would take hours
+    #      and > 150 GB of host RAM on the reference path) -----------------------------------------------------------
+    sub = 8
+    logits, labels = bench_sweep.make_pool(torch.device("cuda"))
+    e8 = deeplab.energy_func(logits[:sub])
+    l8 = labels[:sub]
+    del logits
+    conf8, lab8 = e8.cpu().numpy().reshape(-1), l8.cpu().numpy().astype(np.int64).reshape(-1)
+    t_m8, ref8 = _best_of(lambda: mo.eval_ood_measure(conf8, lab8), reps=1)
+    g_m8_ms, got8 = _gpu_ms(lambda: metric.eval_ood_measure(e8, l8))
+    g_m8_e2e_ms, got8h = _gpu_ms(lambda: metric.eval_ood_measure(conf8, lab8), reps=3)
+    out["cfg4_subset"] = {
+        "workload": f"cfg4/cfg5 metric stage on a subset: {sub} of the sweep pool's images ({sub * px / 1e6:.1f} Mpx), "
+                    "energy score, reference eval_ood_measure flow on the CPU",
+        "cpu": {"metric_s": t_m8, "mpix_s": sub * px / t_m8 / 1e6, "result_hex": hexes(ref8)},
+        "gpu": {"metric_ms_device_inputs": g_m8_ms, "mpix_s_device_inputs": sub * px / g_m8_ms / 1e3,
+                "metric_e2e_ms_host_numpy_inputs": g_m8_e2e_ms, "metric_e2e_mpix_s": sub * px / g_m8_e2e_ms / 1e3,
+                "result_hex": hexes(got8)},
+        "metric_equal": hexes(got8) == hexes(ref8) == hexes(got8h),
+        "metric_stage_speedup_e2e": t_m8 * 1e3 / g_m8_e2e_ms,
+    }
+    return out
+
+
+def cub_yardstick(sizes):
+    """cub::DeviceRadixSort on the same box (tools/cub_yardstick, a standalone binary that is NOT part of the library),
+    so the repo's own sort has an external anchor; torch.sort (CUB pairs with int64 indices) when it was not built."""
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "cub_yardstick")
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe] + [str(n) for n in sizes], capture_output=True, text=True, timeout=120)
+            rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+            if rows:
+                return {"source": "tools/cub_yardstick (cub::DeviceRadixSort, CUDA 12.9 CUB)", "rows": rows}
+        except Exception as e:
+            err = repr(e)
+    rows = []
+    for n in sizes:
+        k = torch.randint(-2 ** 31, 2 ** 31 - 1, (n,), device="cuda", dtype=torch.int32)
+        torch.sort(k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.sort(k)
+        e1.record()
+        torch.cuda.synchronize()
+        rows.append({"n": n, "torch_sort_ms": e0.elapsed_time(e1), "torch_sort_gkeys_s": n / e0.elapsed_time(e1) / 1e6})
+    return {"source": "torch.sort (CUB SortPairs with int64 indices: a weaker yardstick)", "rows": rows}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,7 +568,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the metrics / M2F side measurements")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the cfg-4 evaluation sweep (extra.eval_sweep)")
+    ap.add_argument("--sweep-images", type=int, default=2000, help="images of the cfg-4 sweep (BASELINE: 2000)")
+    ap.add_argument("--continuous-frames", type=int, default=256, help="frames of the T ~= N metric-stage variant")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -455,22 +630,49 @@ def main():
     e2e_value = px_per_step * e2e_steps / e2e_ms / 1e3
     torch.cuda.synchronize()
     same = all(torch.equal(h_out[k], out[k].cpu()) for k in WHICH)
-    del h_logits, scratch
+    del scratch
+
+    # the box's own ceiling for that step: the SAME bytes (2.55 GB in, 0.40 GB out per GPU) as plain pinned copies on two
+    # streams, no kernel, all ranks at once -- what the host fabric gives N concurrent GPUs
+    side = torch.cuda.Stream()
+    d_in = logits
+    d_out = [out[k] for k in WHICH]
+
+    def copy_step():
+        d_in.copy_(h_logits, non_blocking=True)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for k, t in zip(WHICH, d_out):
+                h_out[k].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(side)
+
+    def h2d_step():
+        d_in.copy_(h_logits, non_blocking=True)
+
+    for _ in range(2):
+        copy_step()
+    copy_ms = timed(copy_step, 5, dist) / 5
+    h2d_ms = timed(h2d_step, 5, dist) / 5
+    h2d_bytes = B_PER_GPU * C * H * W * 4
+    del h_logits, h_out, d_in, d_out
 
     line = {
         "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "classes": C, "frame": [H, W],
-                   "l2": "input 2.55 GB per step >> 126 MB L2, no flush needed",
-                   "parallelism": f"images sharded over {world} GPU(s), no data-path collective"},
+        "config": common_config(world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "deeplab_score_vec4_kernel<19,true,false>",
                      "algorithmic_bytes_per_launch": B_PER_GPU * H * W * BYTES_PER_PX, "peak_source": peak_src},
-        "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": B_PER_GPU * C * H * W * 4,
+        "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": B_PER_GPU * H * W * 4 * len(WHICH), "steps": e2e_steps,
                 "ms_per_step": e2e_ms / e2e_steps, "matches_device_path": bool(same),
-                "api": "multishiftseg_b200.deeplab.score_maps_host -> mss_deeplab_score_host (pinned host in/out)"},
+                "api": "multishiftseg_b200.deeplab.score_maps_host -> mss_deeplab_score_host (pinned host in/out)",
+                # all ranks copying at once (max over ranks): the ceiling the host side of this box gives the step
+                "h2d_ceiling_GBs_per_gpu": h2d_bytes / h2d_ms / 1e6,
+                "copy_only_ms_per_step": copy_ms,
+                "copy_only_ceiling_value": px_per_step / copy_ms / 1e3,
+                "frac_of_copy_ceiling": (e2e_value * copy_ms * 1e3) / px_per_step},
         "gpu_launches": launches,
     }
     tr = os.path.join(ROOT, "profiles", "traffic.json")
@@ -479,15 +681,30 @@ def main():
             line["roofline"]["traffic"] = json.load(open(tr)).get("deeplab_score_vec4_kernel")
         except Exception:
             pass
+    del logits, out
+    torch.cuda.empty_cache()
+    extra = {}
+
+    # ---- the real multi-GPU path, at every N: cfg-4 sweep (key-range exchange + integer prefix merge) ------------
+    if not args.no_sweep:
+        import bench_sweep
+        env = bench_sweep.Env(dist, rank, world, local)
+        try:
+            sweep = bench_sweep.run_cfg4(env, args.sweep_images, steps=3, warmup=1, oracle_check=True)
+            cont = bench_sweep.run_continuous(env, args.continuous_frames, steps=3, warmup=1)
+            if rank == 0:
+                extra["eval_sweep"] = sweep
+                extra["eval_sweep"]["continuous"] = cont
+        except Exception as e:   # side measurements must never take the headline down
+            if rank == 0:
+                extra["eval_sweep"] = {"error": repr(e)}
 
     if rank == 0 and world == 1 and not args.no_extra:
         try:
-            del logits, out
-            torch.cuda.empty_cache()
-            line["extra"] = {"metrics": extra_metrics_stage(), "m2f": extra_m2f(), "confusion": extra_confusion(),
-                             "head": extra_head(), "mask_gemm": extra_mask_gemm(), "backward": extra_backward()}
-        except Exception as e:   # side measurements must never take the headline down
-            line["extra"] = {"error": repr(e)}
+            extra.update({"metrics": extra_metrics_stage(), "m2f": extra_m2f(), "confusion": extra_confusion(),
+                          "head": extra_head(), "mask_gemm": extra_mask_gemm(), "backward": extra_backward()})
+        except Exception as e:
+            extra["error"] = repr(e)
     if sampler is not None:
         line["clocks"] = sampler.summary()
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -496,6 +713,12 @@ def main():
         line["cpu_baseline"] = {"value": mpix, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{reps} passes over 2 of the 16 images (1024x2048) in {el:.1f} s, torch-CPU "
                                           "restatement of deepv3.py:251-253 + max-logit + entropy (oracle/scoring_oracle.py)"}
+        try:
+            extra["cpu_legs"] = cpu_legs()
+        except Exception as e:
+            extra["cpu_legs"] = {"error": repr(e)}
+    if extra:
+        line["extra"] = extra
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -171,6 +171,165 @@ def main5(args, world, rank, local, dist):
         dist.destroy_process_group()
 
 
+class Env:
+    """Process / device context shared by bench.py and bench_sweep.py (one process per GPU)."""
+
+    def __init__(self, dist, rank, world, local):
+        self.dist, self.rank, self.world, self.local = dist, rank, world, local
+        self.dev = torch.device("cuda", local)
+
+    def sync_all(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        t = torch.tensor(vals, device=self.dev, dtype=torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def sum_over_ranks(self, v):
+        t = torch.tensor([v], device=self.dev, dtype=torch.int64)
+        if self.dist is not None:
+            self.dist.all_reduce(t)
+        return int(t.item())
+
+
+def _timed_steps(env, step, steps, warmup):
+    """`step()` -> (result, score_ms, metric_ms).  Device-timed, max over ranks per step, mean over steps."""
+    from multishiftseg_b200 import _lib as L
+    for _ in range(max(warmup, 1)):
+        step()
+    times, score_ms, metric_ms, res = [], [], [], None
+    l0 = L.launch_count()
+    for _ in range(steps):
+        env.sync_all()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        res, a, b = step()
+        t1.record()
+        torch.cuda.synchronize()
+        t, a, b = env.max_over_ranks([t0.elapsed_time(t1), a, b])
+        times.append(t); score_ms.append(a); metric_ms.append(b)
+    launches = env.sum_over_ranks(L.launch_count() - l0)
+    mean = lambda x: sum(x) / len(x)
+    return res, mean(times), mean(score_ms), mean(metric_ms), launches
+
+
+def run_cfg4(env, images=2000, steps=3, warmup=1, oracle_check=True):
+    """cfg-4: `images` frames = images/16 copies of a 16-image pool, fused energy scoring + append per batch, ONE exact
+    global metric.  Returns the result dict (rank 0; None elsewhere).  `bit_exact_vs_pool` is computed inside the run:
+    sweep result == the pool evaluated once on one GPU == (oracle_check) the CPU oracle on the pool's score map."""
+    from multishiftseg_b200.evaluator import StreamingEvaluator
+    dev, rank, world = env.dev, env.rank, env.world
+    logits, labels = make_pool(dev)
+    batches = max(1, images // POOL)
+    images = batches * POOL
+    my_batches = len(range(rank, batches, world))                   # batch j -> rank j % world
+    ev = StreamingEvaluator(capacity=max(my_batches, 1) * POOL * H * W, device=dev, distributed=(world > 1))
+
+    def step():
+        ev.reset()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        for _ in range(my_batches):
+            ev.update_from_logits(logits, labels, key="energy", which=("energy",))
+        e[1].record()
+        res = ev.compute()
+        e[2].record()
+        torch.cuda.synchronize()
+        return res, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+
+    res, ms, score_ms, metric_ms, launches = _timed_steps(env, step, steps, warmup)
+    exchange = getattr(ev, "last_exchange", None)
+    del ev
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    # the pool once, single GPU, same kernels: replication leaves the float64 results bit-identical
+    single = StreamingEvaluator(capacity=POOL * H * W, device=dev, distributed=False)
+    energy = single.update_from_logits(logits, labels, key="energy", which=("energy",))["energy"]
+    ref = single.compute()
+    hexes = [float(v).hex() for v in res]
+    pool_hex = [float(v).hex() for v in ref]
+    out = {
+        "workload": f"cfg4: {images} images 1024x2048 (= {batches} x the 16-image pool), fused energy scoring + append, "
+                    "one exact AUROC/AP/FPR95 over all valid pixels; labels 90/5/5 % ID/OOD/ignore",
+        "images": images, "n_gpus": world, "steps": steps, "scaling": "strong",
+        "images_s": images / ms * 1e3, "mpix_s": images * H * W / ms / 1e3, "ms_per_step": ms,
+        "phases_ms": {"score_and_append": score_ms, "global_metric": metric_ms},
+        "result": [float(v) for v in res], "result_hex": hexes, "pool_result_hex": pool_hex,
+        "matches_single_pool": pool_hex == hexes, "gpu_launches": launches,
+    }
+    if oracle_check:
+        from oracle import c_oracle                                   # the checker, never the thing measured
+        want = c_oracle.eval_ood_measure(energy.cpu().numpy(), labels.cpu().numpy())
+        out["oracle_result_hex"] = [float(v).hex() for v in want]
+        out["pool_matches_oracle"] = out["oracle_result_hex"] == pool_hex
+        out["bit_exact_vs_pool"] = bool(out["matches_single_pool"] and out["pool_matches_oracle"])
+    else:
+        out["bit_exact_vs_pool"] = bool(out["matches_single_pool"])
+    if world > 1 and exchange:
+        out["exchange"] = {"kind": exchange["exchange"], "recv_keys_rank0": [int(sum(c)) for c in exchange["recv_counts"]],
+                           "thresholds_per_rank": exchange["thresholds_per_rank"],
+                           "phase_ms_rank0": {k: round(v, 3) for k, v in exchange.get("phase_ms", {}).items()}}
+    return out
+
+
+def run_continuous(env, images=256, steps=3, warmup=1):
+    """T ~= N variant of the sweep's metric stage: `images` frames of i.i.d. continuous scores (no replication, so
+    nearly every valid pixel is its own threshold -- the worst case for the float64 tail), appended frame by frame and
+    evaluated once.  Frame j is generated from seed 9000 + j whatever the world size, so result_hex is comparable
+    across N."""
+    from multishiftseg_b200.evaluator import StreamingEvaluator
+    dev, rank, world = env.dev, env.rank, env.world
+    mine = list(range(rank, images, world))
+    ev = StreamingEvaluator(capacity=max(len(mine), 1) * H * W, device=dev, distributed=(world > 1))
+    g = torch.Generator(device=dev)
+
+    def frame(j):
+        g.manual_seed(9000 + j)
+        r = torch.rand(H * W, device=dev, generator=g)
+        lab = torch.zeros(H * W, dtype=torch.uint8, device=dev)
+        lab[r < 0.05] = 1
+        lab[r > 0.95] = 255
+        s = torch.randn(H * W, device=dev, generator=g) + (lab == 1) * 1.5
+        return s, lab
+
+    def fill():
+        ev.reset()
+        for j in mine:
+            ev.update(*frame(j))
+
+    def step():
+        fill()                                                       # generation + append: not the measured part
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e[0].record()
+        res = ev.compute()
+        e[1].record()
+        torch.cuda.synchronize()
+        return res, 0.0, e[0].elapsed_time(e[1])
+
+    res, _, _, metric_ms, _ = _timed_steps(env, step, steps, warmup)
+    exchange = getattr(ev, "last_exchange", None)
+    fill()
+    m = env.sum_over_ranks(ev.backend.state(ev.buf)[0])
+    del ev
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    out = {"workload": f"{images} frames 1024x2048 of continuous i.i.d. scores (T ~= N): exact AUROC/AP/FPR95 of scores "
+                       "already in the evaluator (metric stage only)",
+           "valid_keys": m, "n_gpus": world, "metric_ms": metric_ms, "gkeys_s": m / metric_ms / 1e6,
+           "gpix_s": images * H * W / metric_ms / 1e6, "result_hex": [float(v).hex() for v in res]}
+    if world > 1 and exchange:
+        out["thresholds"] = int(sum(exchange["thresholds_per_rank"]))
+        out["phase_ms_rank0"] = {k: round(v, 3) for k, v in exchange.get("phase_ms", {}).items()}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +337,8 @@ def main():
     ap.add_argument("--images", type=int, default=2000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--continuous", type=int, default=0, help="also run the T ~= N metric-stage variant on this many frames")
+    ap.add_argument("--no-oracle", action="store_true")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_sweep.py needs a B200: there is no CPU fallback for the product path")
@@ -196,79 +357,21 @@ def main():
     if args.cfg == 5:
         return main5(args, world, rank, local, dist)
 
-    from multishiftseg_b200 import _lib as L
-    from multishiftseg_b200.evaluator import StreamingEvaluator
-    dev = torch.device("cuda", local)
-    logits, labels = make_pool(dev)
-    batches = max(1, args.images // POOL)
-    images = batches * POOL
-    my_batches = len(range(rank, batches, world))                   # batch j -> rank j % world
-    ev = StreamingEvaluator(capacity=max(my_batches, 1) * POOL * H * W, device=dev, distributed=(world > 1))
-
-    def sync_all():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step():
-        ev.reset()
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        e[0].record()
-        for _ in range(my_batches):
-            ev.update_from_logits(logits, labels, key="energy", which=("energy",))
-        e[1].record()
-        res = ev.compute()
-        e[2].record()
-        torch.cuda.synchronize()
-        return res, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
-
-    for _ in range(max(args.warmup, 1)):
-        step()
-    times, score_ms, metric_ms, res = [], [], [], None
-    l0 = L.launch_count()
-    for _ in range(args.steps):
-        sync_all()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        res, a, b = step()
-        t1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([t0.elapsed_time(t1), a, b], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        times.append(float(t[0])); score_ms.append(float(t[1])); metric_ms.append(float(t[2]))
-    launches = L.launch_count() - l0
-    if dist is not None:
-        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(lt)
-        launches = int(lt.item())
-    ms = sum(times) / len(times)
-
+    env = Env(dist, rank, world, local)
+    r = run_cfg4(env, args.images, args.steps, args.warmup, oracle_check=not args.no_oracle)
+    c = run_continuous(env, args.continuous, args.steps, args.warmup) if args.continuous else None
     if rank == 0:
-        # the pool once, single GPU, same kernels: replication leaves the float64 results bit-identical
-        single = StreamingEvaluator(capacity=POOL * H * W, device=dev, distributed=False)
-        single.update_from_logits(logits, labels, key="energy", which=("energy",))
-        ref = single.compute()
-        hexes = [float(v).hex() for v in res]
         line = {
             "metric": "eval images/s (cfg4: fused DeepLab energy scoring + exact AUROC/AP/FPR95 over the whole dataset)",
-            "value": images / ms * 1e3, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "value": r["images_s"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "dtype": "f32 scores, u32 keys, i64 counts, f64 tail", "data": "synthetic",
-            "config": {"workload": f"cfg4: {images} images 1024x2048 (= {batches} x the 16-image pool), "
-                                   "energy score, labels 90/5/5 % ID/OOD/ignore",
+            "config": {"workload": r["workload"],
                        "parallelism": f"batches sharded over {world} GPU(s); one key-range exchange for the global metric"},
-            "mpix_s": images * H * W / ms / 1e3,
-            "phases_ms": {"score_and_append": sum(score_ms) / len(score_ms), "global_metric": sum(metric_ms) / len(metric_ms)},
-            "result": [float(v) for v in res], "result_hex": hexes,
-            "matches_single_pool": [float(v).hex() for v in ref] == hexes,
-            "gpu_launches": launches,
         }
-        if world > 1 and getattr(ev, "last_exchange", None):
-            x = ev.last_exchange
-            line["exchange"] = {"recv_pairs_rank0": int(sum(x["recv_counts"])), "thresholds_per_rank": x["thresholds_per_rank"],
-                                "phase_ms_rank0": {k: round(v, 3) for k, v in x.get("phase_ms", {}).items()}}
+        line.update({k: v for k, v in r.items() if k not in ("workload", "n_gpus", "steps", "scaling", "ms_per_step")})
+        if c:
+            line["continuous"] = c
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MSS_ABI_VERSION 1
+#define MSS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MSS_API __attribute__((visibility("default")))
@@ -68,20 +68,24 @@ MSS_API int64_t mss_launch_count(void);
  * append of order-preserving keys for the valid pixels only).
  * ------------------------------------------------------------------------------------------- */
 #define MSS_EVAL_STATE_BYTES 64
+/* Two key-only streams in ONE key buffer (ABI 2; ABI 1 stored (key, u8 label) pairs): the 0/1 label of a valid pixel
+ * is the stream its key lives in, so no label byte is stored, sorted or exchanged between GPUs. */
 typedef struct mss_eval_buffers {
-    uint32_t *keys;     /* [capacity] ascending key order == descending float32 score; -0.0 == +0.0 */
-    uint8_t *labs;      /* [capacity] 0 = in-distribution, 1 = OOD */
-    void *state;        /* MSS_EVAL_STATE_BYTES device bytes: {u64 count, u64 n_pos, u32 nan, u32 inf, ...} */
-    int64_t capacity;   /* in elements */
+    uint32_t *keys;     /* [capacity] ascending key order == descending float32 score; -0.0 == +0.0.
+                         * in-distribution keys fill keys[0, n_neg) upwards,
+                         * OOD keys fill keys[capacity - n_pos, capacity) downwards */
+    void *state;        /* MSS_EVAL_STATE_BYTES device bytes: {u64 n_neg, u64 n_pos, u32 nan, u32 inf, u64 dropped, ...} */
+    int64_t capacity;   /* in elements; n_neg + n_pos <= capacity */
 } mss_eval_buffers;
 
 /* zero the state (count = 0) */
 MSS_API int mss_eval_reset(const mss_eval_buffers *ev, void *stream);
 /* metric.py:171-172 selection (label == id_in / id_out, everything else ignored) + key build; appends
- * the valid pixels of (scores, labels)[0..n) to ev (order inside the buffer is unspecified). */
+ * the valid pixels of (scores, labels)[0..n) to ev (order inside a stream is unspecified). */
 MSS_API int mss_eval_append(const float *scores, const void *labels, int label_dtype, int64_t n,
                     int64_t id_in, int64_t id_out, const mss_eval_buffers *ev, void *stream);
-/* read back {count, n_pos, nan_flag, inf_flag} (synchronises the stream) */
+/* read back {count = n_neg + n_pos, n_pos, nan_flag, inf_flag} (synchronises the stream);
+ * MSS_ERR_WORKSPACE when the capacity was exceeded */
 MSS_API int mss_eval_state_host(const mss_eval_buffers *ev, int64_t out_host[4], void *stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -196,17 +200,23 @@ MSS_API int mss_ood_metrics(const float *scores, const void *labels, int label_d
                     int64_t id_in, int64_t id_out, void *workspace, size_t workspace_bytes,
                     double out_host[3], int64_t counts_host[4], void *stream);
 
-/* same, from keys accumulated in an evaluator (keys/labs are sorted in place). */
+/* same, from the keys accumulated in an evaluator (both streams are sorted in place).
+ * workspace >= mss_ood_metrics_from_eval_workspace_bytes(count), count = mss_eval_state_host()[0]. */
+MSS_API size_t mss_ood_metrics_from_eval_workspace_bytes(int64_t count);
 MSS_API int mss_ood_metrics_from_eval(const mss_eval_buffers *ev, void *workspace, size_t workspace_bytes,
                               double out_host[3], int64_t counts_host[4], void *stream);
 
 /* ---- stage-level entry points (used by the multi-GPU evaluator, which interleaves them with
- * NCCL collectives issued through torch.distributed) ---------------------------------------- */
-/* stable LSD radix sort of n (key, label) pairs, ascending key, in place (uses workspace as the
- * second buffer). */
-MSS_API size_t mss_sort_pairs_workspace_bytes(int64_t n);
-MSS_API int mss_sort_pairs(uint32_t *keys, uint8_t *labs, int64_t n, void *workspace, size_t workspace_bytes,
-                   void *stream);
+ * collectives issued through torch.distributed) ------------------------------------------------ */
+/* stable LSD radix sort (onesweep, key-only) of two independent key arrays, ascending, in place, by one sequence
+ * of launches (the second array may be NULL / empty).  workspace: mss_sort_keys_workspace_bytes(n_a + n_b). */
+MSS_API size_t mss_sort_keys_workspace_bytes(int64_t n_total);
+MSS_API int mss_sort_keys(uint32_t *keys_a, int64_t n_a, uint32_t *keys_b, int64_t n_b, void *workspace,
+                  size_t workspace_bytes, void *stream);
+/* the same for the two streams of an evaluator; the stream sizes are read from the DEVICE state (no host round
+ * trip), n_upper >= n_neg + n_pos sizes the grids.  workspace: mss_sort_keys_workspace_bytes(n_upper). */
+MSS_API int mss_eval_sort(const mss_eval_buffers *ev, int64_t n_upper, void *workspace, size_t workspace_bytes,
+                  void *stream);
 /* histogram of the top `bits` (<= 16) key bits: hist[1 << bits] int64, overwritten (splitter selection) */
 MSS_API int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int64_t *hist, void *stream);
 /* same over a systematic sample: only every `every`-th group of 4 consecutive keys is counted (every >= 1).
@@ -214,35 +224,35 @@ MSS_API int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int64_
  * so the multi-GPU evaluator histograms ~2^24 keys per rank instead of all of them. */
 MSS_API int mss_keys_histogram_sampled(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist,
                                void *stream);
-/* stable partition of (key,label) pairs into `parts` (<= 256) destination ranges:
+/* stable partition of keys into `parts` (<= 256) destination ranges:
  * dest(key) = #{ j : key >= splitters[j] }, splitters ascending device array [parts-1].
  * out_counts_host[parts] receives the bucket sizes (synchronises the stream). */
-MSS_API size_t mss_partition_workspace_bytes(int64_t n);
-MSS_API int mss_partition_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n, const uint32_t *splitters,
-                        int parts, uint32_t *keys_out, uint8_t *labs_out, int64_t *out_counts_host,
-                        void *workspace, size_t workspace_bytes, void *stream);
-/* bucket sizes only (same dest rule as mss_partition_pairs); workspace >= 2048 bytes; synchronises the stream */
+MSS_API size_t mss_partition_workspace_bytes(int64_t n, int parts);
+MSS_API int mss_partition_keys(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
+                       uint32_t *keys_out, int64_t *out_counts_host, void *workspace, size_t workspace_bytes,
+                       void *stream);
+/* bucket sizes only (same dest rule as mss_partition_keys); workspace >= 2048 bytes; synchronises the stream */
 MSS_API int mss_partition_count(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
                         int64_t *out_counts_host, void *workspace, size_t workspace_bytes, void *stream);
-/* Fused partition + exchange: the same stable partition, but bucket d is stored straight into ITS OWN pair of
- * buffers -- typically the receive buffers of GPU d, mapped into this process (peer / symmetric memory), so the
- * stores travel over NVLink and no NCCL all-to-all and no local staging copy is needed.
- *   dst_keys_host[d], dst_labs_host[d]  device addresses (as integers) of bucket d's uint32 / uint8 buffers
- *   dst_offsets_host[d]                 element offset inside them where this rank's block starts
+/* Fused partition + exchange: the same stable partition, but bucket d is stored straight into ITS OWN buffer --
+ * typically the receive buffer of GPU d, mapped into this process (peer / symmetric memory), so the stores travel
+ * over NVLink and no NCCL all-to-all and no local staging copy is needed.  Only 4-byte key stores cross the link.
+ *   dst_keys_host[d]     device address (as an integer) of bucket d's uint32 buffer
+ *   dst_offsets_host[d]  element offset inside it where this rank's block starts
  * The caller sizes the blocks with mss_partition_count (+ an all-gather across ranks) and must order this call
- * against the peers' use of the buffers (barrier before and after).  workspace: mss_partition_workspace_bytes(n).
+ * against the peers' use of the buffers (barrier before and after).  workspace: mss_partition_workspace_bytes(n, parts).
  * Synchronises the stream. */
-MSS_API int mss_partition_scatter_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n,
-                                const uint32_t *splitters, int parts, const uint64_t *dst_keys_host,
-                                const uint64_t *dst_labs_host, const int64_t *dst_offsets_host,
-                                void *workspace, size_t workspace_bytes, void *stream);
-/* sorted pairs -> per distinct key cumulative counts: tps[k] = pos_before + #pos at positions <= end_k,
- * fps[k] = idx_before + end_k + 1 - tps[k] (int64).  tps/fps need room for n entries.  *T_host = number
- * of distinct keys, pn_host = {#pos, #neg} of this slice (synchronises the stream). */
+MSS_API int mss_partition_scatter_keys(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
+                               const uint64_t *dst_keys_host, const int64_t *dst_offsets_host,
+                               void *workspace, size_t workspace_bytes, void *stream);
+/* two sorted key arrays (negatives = in-distribution, positives = OOD) -> per distinct key of their union the
+ * cumulative counts  tps[k] = pos_before + #{positives with key <= key_k},  fps[k] = neg_before + #{negatives with
+ * key <= key_k}  (int64; one merge-path pass).  tps/fps need room for n_neg + n_pos entries.  *T_host = number of
+ * distinct keys (synchronises the stream). */
 MSS_API size_t mss_counts_workspace_bytes(int64_t n);
-MSS_API int mss_counts_from_sorted(const uint32_t *keys, const uint8_t *labs, int64_t n, int64_t pos_before,
-                           int64_t idx_before, int64_t *tps, int64_t *fps, int64_t *T_host,
-                           int64_t pn_host[2], void *workspace, size_t workspace_bytes, void *stream);
+MSS_API int mss_counts_from_sorted(const uint32_t *neg_keys, int64_t n_neg, const uint32_t *pos_keys, int64_t n_pos,
+                           int64_t pos_before, int64_t neg_before, int64_t *tps, int64_t *fps, int64_t *T_host,
+                           void *workspace, size_t workspace_bytes, void *stream);
 /* float64 tail over device int64 (tps, fps)[T]: out_host = {AUROC, AP, FPR95}; *T_roc_host = points kept
  * by roc_curve(drop_intermediate=True).  recall_level is 0.95 everywhere in the reference
  * (metric.py:130).  Replays numpy's pairwise summation tree exactly. */
@@ -268,8 +278,8 @@ MSS_API int mss_pairwise_sum_host(const double *terms_host, int64_t n, double *o
  * `hist += d['hist']; correct += ...; labeled += ...` loop (:21-33) kept on the device:
  *   hist [n_cl * n_cl] int64 (row = gt, column = pred), labeled_correct [3] int64 = {labeled, correct,
  *   out-of-range count}.  n_cl <= 32.  A labeled pixel whose n_cl*gt + pred falls outside [0, n_cl^2)
- * makes numpy raise; here it is counted in labeled_correct[2] and the call returns MSS_ERR_INVALID_ARG.
- * Both calls synchronise `stream` (to read that flag).
+ * makes numpy raise; here it is counted in labeled_correct[2] and reported (MSS_ERR_INVALID_ARG) by
+ * mss_confusion_result.  The two update calls only enqueue work: a streaming evaluation synchronises once, at the end.
  * ------------------------------------------------------------------------------------------- */
 /* pred, gt: class-index maps [n] of MSS_LABEL_* element types */
 MSS_API int mss_confusion_hist(const void *pred, int pred_dtype, const void *gt, int gt_dtype, int64_t n,
@@ -279,6 +289,15 @@ MSS_API int mss_confusion_hist(const void *pred, int pred_dtype, const void *gt,
 MSS_API int mss_confusion_from_logits(const float *logits, int64_t B, int C, int64_t HW, const void *gt,
                               int gt_dtype, int n_cl, int64_t *hist, int64_t *labeled_correct,
                               void *stream);
+
+/* accumulators -> host (one D2H copy, synchronises): hist_host [n_cl * n_cl], labeled_correct_host = {labeled, correct} */
+MSS_API int mss_confusion_result(const int64_t *hist, const int64_t *labeled_correct, int n_cl, int64_t *hist_host,
+                         int64_t labeled_correct_host[2], void *stream);
+/* host-only (no device work): compute_score (metric.py:42-49; per_class = 0) / compute_score_per_class (:51-64;
+ * per_class = 1) on the float64 confusion accumulator of compute_metric (:22), operation by operation as numpy does it:
+ *   iu_host [n_cl], class_acc_host [n_cl] (per_class only), out_host = {mean_IU, mean_IU_no_back | nan, mean_pixel_acc} */
+MSS_API int mss_confusion_scores(const double *hist_host, int n_cl, double correct, double labeled, int per_class,
+                         double *iu_host, double *class_acc_host, double out_host[3]);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points: what a reference-side caller holding numpy / CPU tensors would call.

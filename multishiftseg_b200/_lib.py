@@ -38,7 +38,7 @@ class MssError(RuntimeError):
 
 
 class EvalBuffers(C.Structure):
-    _fields_ = [("keys", C.c_void_p), ("labs", C.c_void_p), ("state", C.c_void_p), ("capacity", C.c_int64)]
+    _fields_ = [("keys", C.c_void_p), ("state", C.c_void_p), ("capacity", C.c_int64)]
 
 
 _p, _i, _i64, _u, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_size_t, C.c_double
@@ -67,23 +67,27 @@ SIGNATURES = {
     "mss_m2f_mask_logits": (_i, [_p, _p, _i64, _i, _i, _i64, _p, _p, _sz, _p]),
     "mss_ood_metrics_workspace_bytes": (_sz, [_i64]),
     "mss_ood_metrics": (_i, [_p, _p, _i, _i64, _i64, _i64, _p, _sz, _p, _p, _p]),
+    "mss_ood_metrics_from_eval_workspace_bytes": (_sz, [_i64]),
     "mss_ood_metrics_from_eval": (_i, [_EV, _p, _sz, _p, _p, _p]),
-    "mss_sort_pairs_workspace_bytes": (_sz, [_i64]),
-    "mss_sort_pairs": (_i, [_p, _p, _i64, _p, _sz, _p]),
+    "mss_sort_keys_workspace_bytes": (_sz, [_i64]),
+    "mss_sort_keys": (_i, [_p, _i64, _p, _i64, _p, _sz, _p]),
+    "mss_eval_sort": (_i, [_EV, _i64, _p, _sz, _p]),
     "mss_keys_histogram": (_i, [_p, _i64, _i, _p, _p]),
     "mss_keys_histogram_sampled": (_i, [_p, _i64, _i, _i, _p, _p]),
-    "mss_partition_workspace_bytes": (_sz, [_i64]),
-    "mss_partition_pairs": (_i, [_p, _p, _i64, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "mss_partition_workspace_bytes": (_sz, [_i64, _i]),
+    "mss_partition_keys": (_i, [_p, _i64, _p, _i, _p, _p, _p, _sz, _p]),
     "mss_partition_count": (_i, [_p, _i64, _p, _i, _p, _p, _sz, _p]),
-    "mss_partition_scatter_pairs": (_i, [_p, _p, _i64, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "mss_partition_scatter_keys": (_i, [_p, _i64, _p, _i, _p, _p, _p, _sz, _p]),
     "mss_counts_workspace_bytes": (_sz, [_i64]),
-    "mss_counts_from_sorted": (_i, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "mss_counts_from_sorted": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "mss_tail_workspace_bytes": (_sz, [_i64]),
     "mss_metrics_tail": (_i, [_p, _p, _i64, _d, _p, _sz, _p, _p, _p]),
     "mss_pairwise_leaf_bounds": (_i, [_i64, _i64, _p, _p, _p]),
     "mss_pairwise_sum_host": (_i, [_p, _i64, _p]),
     "mss_confusion_hist": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p, _p]),
     "mss_confusion_from_logits": (_i, [_p, _i64, _i, _i64, _p, _i, _i, _p, _p, _p]),
+    "mss_confusion_result": (_i, [_p, _p, _i, _p, _p, _p]),
+    "mss_confusion_scores": (_i, [_p, _i, _d, _d, _i, _p, _p, _p]),
     "mss_deeplab_score_host_scratch_bytes": (_sz, [_i64, _i, _i64, _u]),
     "mss_deeplab_score_host": (_i, [_p, _i64, _i, _i64, _u, _p, _p, _p, _p, _p, _sz, _p]),
 }
@@ -136,6 +140,16 @@ def require_cuda(t: torch.Tensor, name: str) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise MssError(f"{name} must be a CUDA tensor: this path runs on the GPU only (no CPU fallback)")
     return t
+
+
+def forbid_grad(what: str, *tensors):
+    """Entry points without a backward kernel refuse inputs that autograd is tracking: returning a tensor with no
+    grad_fn would let a training loop (train_m2f.py:443 -> criterion -> loss.backward()) run with silently missing
+    gradients.  Wrap the call in torch.no_grad() for inference, or detach the inputs."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise MssError(f"{what} has no backward kernel: its inputs require grad and autograd is enabled. "
+                       "Call it under torch.no_grad() (evaluation), or detach() the inputs; the differentiable "
+                       "entry points are deeplab.energy_func / Upsample / anomaly_score.")
 
 
 def ptr(t):

@@ -46,6 +46,17 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 int sm_count();  // SMs of the current device (148 on B200), cached per device
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: a call site keeps one bit per device
+// ordinal (a process may drive several GPUs, e.g. nn.DataParallel threads) instead of one process-wide flag.
+inline bool first_use_on_device(std::atomic<unsigned long long> &seen) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen.load(std::memory_order_acquire) & bit) return false;
+    seen.fetch_or(bit, std::memory_order_acq_rel);     // (two threads may both set the attribute once: harmless)
+    return true;
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // bump allocator over a caller-provided workspace
@@ -64,9 +75,12 @@ struct Carver {
 };
 
 // ---- evaluator state (device) -----------------------------------------------------------------
+// Two key-only streams share ONE key buffer: in-distribution (negative) keys fill keys[0, n_neg) upwards, OOD
+// (positive) keys fill keys[capacity - n_pos, capacity) downwards.  The 0/1 label is the stream a key lives in, so no
+// label byte is ever stored, sorted or exchanged.
 struct EvalState {
-    unsigned long long count;  // valid pixels appended so far
-    unsigned long long n_pos;  // of which OOD
+    unsigned long long n_neg;  // in-distribution pixels appended so far
+    unsigned long long n_pos;  // OOD pixels appended so far
     unsigned int nan_flag;
     unsigned int inf_flag;
     unsigned long long overflow;  // appends dropped because capacity was exceeded
@@ -157,6 +171,47 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+}
+
+// ---- decoupled look-back status words (sort passes, counting passes) ------------------------------------------
+// bits 63..62 = 0 empty / 1 tile aggregate / 2 inclusive prefix, low 62 bits = value
+constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL_MASK = (1ull << 62) - 1;
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// One value per tile (compaction offsets): called by ALL 32 lanes of one warp; publishes this tile's aggregate,
+// walks back 32 predecessors per round trip until an inclusive prefix is met, publishes the inclusive prefix and
+// returns the exclusive one.  Tiles must be numbered in start order (atomic ticket).
+__device__ __forceinline__ unsigned long long warp_lookback(unsigned long long *status, unsigned tile, unsigned long long tot) {
+    const unsigned lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) st_status(status, FLAG_INC | tot);
+        return 0;
+    }
+    if (lane == 0) st_status(status + tile, FLAG_AGG | tot);
+    unsigned long long prefix = 0;
+    long long base = (long long)tile - 1;
+    for (;;) {
+        const long long idx = base - lane;
+        const unsigned long long st = idx >= 0 ? ld_status(status + idx) : FLAG_INC;     // before tile 0: prefix 0
+        const unsigned flag = (unsigned)(st >> 62);
+        const unsigned inc_m = __ballot_sync(0xffffffffu, flag == 2u), emp_m = __ballot_sync(0xffffffffu, flag == 0u);
+        const unsigned upto = inc_m ? ((2u << (__ffs(inc_m) - 1)) - 1u) : 0xffffffffu;   // lanes up to the first inclusive one
+        if (emp_m & upto) continue;                                                      // a needed predecessor has not published yet
+        unsigned long long v = ((upto >> lane) & 1u) ? (st & VAL_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        prefix += v;
+        if (inc_m) break;
+        base -= 32;
+    }
+    if (lane == 0) st_status(status + tile, FLAG_INC | (prefix + tot));
+    return prefix;
 }
 #endif  // __CUDACC__
 

@@ -197,20 +197,6 @@ static bool label_dtype_ok(int d) { return d == MSS_LABEL_U8 || d == MSS_LABEL_I
 
 using namespace mss;
 
-static int finish_confusion(ConfDev out, void *stream, const char *who) {
-    // out_of_range is sticky in the accumulator: report it like numpy would (bincount / reshape raise)
-    unsigned long long bad = 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    MSS_CHECK_CUDA(cudaMemcpyAsync(&bad, out.lc + 2, 8, cudaMemcpyDeviceToHost, st));
-    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
-    if (bad) {
-        set_error("%s: %llu labeled pixel(s) with n_cl*gt + pred outside [0, n_cl^2) (numpy's bincount/reshape raises)",
-                  who, bad);
-        return MSS_ERR_INVALID_ARG;
-    }
-    return MSS_OK;
-}
-
 extern "C" int mss_confusion_hist(const void *pred, int pred_dtype, const void *gt, int gt_dtype, int64_t n, int n_cl,
                                   int64_t *hist, int64_t *labeled_correct, void *stream) {
     MSS_REQUIRE(n >= 0 && n_cl >= 1 && n_cl <= CF_MAX_CL, "mss_confusion_hist: need n >= 0 and 1 <= n_cl <= 32");
@@ -227,7 +213,7 @@ extern "C" int mss_confusion_hist(const void *pred, int pred_dtype, const void *
             (const char *)pred + o * pred_dtype, pred_dtype, (const char *)gt + o * gt_dtype, gt_dtype, m, n_cl, out);
         MSS_CHECK_LAUNCH();
     }
-    return finish_confusion(out, stream, "mss_confusion_hist");
+    return MSS_OK;
 }
 
 extern "C" int mss_confusion_from_logits(const float *logits, int64_t B, int C, int64_t HW, const void *gt,
@@ -251,5 +237,74 @@ extern "C" int mss_confusion_from_logits(const float *logits, int64_t B, int C, 
         confusion_logits_generic_kernel<<<conf_grid(n), CF_THREADS, 0, st>>>(logits, C, HW, n, gt, gt_dtype, n_cl, out);
     }
     MSS_CHECK_LAUNCH();
-    return finish_confusion(out, stream, "mss_confusion_from_logits");
+    return MSS_OK;
+}
+
+// accumulators -> host: the ONE synchronisation of a streaming evaluation (the update calls above only enqueue)
+extern "C" int mss_confusion_result(const int64_t *hist, const int64_t *labeled_correct, int n_cl, int64_t *hist_host,
+                                    int64_t labeled_correct_host[2], void *stream) {
+    MSS_REQUIRE(hist && labeled_correct && hist_host && labeled_correct_host && n_cl >= 1 && n_cl <= CF_MAX_CL,
+                "mss_confusion_result: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long lc[3] = {0, 0, 0};
+    MSS_CHECK_CUDA(cudaMemcpyAsync(hist_host, hist, (size_t)n_cl * n_cl * 8, cudaMemcpyDeviceToHost, st));
+    MSS_CHECK_CUDA(cudaMemcpyAsync(lc, labeled_correct, sizeof(lc), cudaMemcpyDeviceToHost, st));
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    labeled_correct_host[0] = lc[0];
+    labeled_correct_host[1] = lc[1];
+    if (lc[2]) {
+        // numpy's bincount / reshape raise on the first batch that has such a pixel (metric.py:15-17)
+        set_error("mss_confusion_result: %lld labeled pixel(s) with n_cl*gt + pred outside [0, n_cl^2) (numpy's bincount/reshape raises)",
+                  lc[2]);
+        return MSS_ERR_INVALID_ARG;
+    }
+    return MSS_OK;
+}
+
+// np.nanmean over a short float64 vector: NaNs count as 0 in the sum (numpy's pairwise order) and not in the divisor
+static double np_nanmean(const double *a, int n) {
+    double tmp[CF_MAX_CL];
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+        const bool is_nan = a[i] != a[i];
+        tmp[i] = is_nan ? 0.0 : a[i];
+        cnt += !is_nan;
+    }
+    double tot = 0.0;
+    if (n > 0) mss_pairwise_sum_host(tmp, n, &tot);
+    volatile double r = tot / (double)cnt;       // 0 / 0 -> nan ("Mean of empty slice" in numpy)
+    return r;
+}
+
+// host-only: the closed-form arithmetic of compute_score (metric.py:42-49; per_class = 0) and compute_score_per_class
+// (metric.py:51-64; per_class = 1) on the accumulated confusion matrix, IEEE float64 operation by operation as numpy
+// evaluates it.  hist_host is the float64 accumulator of compute_metric (metric.py:22), row = gt, column = pred.
+//   iu_host [n_cl]          per-class IoU
+//   class_acc_host [n_cl]   per-class accuracy (per_class = 1 only; may be NULL otherwise)
+//   out_host = {mean_IU, mean_IU_no_back (per_class = 0) or nan, mean_pixel_acc}
+extern "C" int mss_confusion_scores(const double *hist_host, int n_cl, double correct, double labeled, int per_class,
+                                    double *iu_host, double *class_acc_host, double out_host[3]) {
+    MSS_REQUIRE(hist_host && iu_host && out_host && n_cl >= 1 && n_cl <= CF_MAX_CL, "mss_confusion_scores: bad arguments");
+    MSS_REQUIRE(!per_class || class_acc_host, "mss_confusion_scores: per_class needs class_acc_host");
+    for (int c = 0; c < n_cl; c++) {
+        double row = 0.0, col = 0.0;             // integer-valued float64 sums: exact in any order
+        for (int j = 0; j < n_cl; j++) { row += hist_host[c * n_cl + j]; col += hist_host[j * n_cl + c]; }
+        const double inter = hist_host[c * n_cl + c];
+        volatile double uni = row + col;
+        uni = uni - inter;
+        if (per_class) {
+            volatile double q = inter / (uni > 1.0 ? (double)uni : 1.0);
+            iu_host[c] = q;
+            volatile double a = inter / (row > 1.0 ? row : 1.0);
+            class_acc_host[c] = a;
+        } else {
+            volatile double q = inter / uni;     // 0 / 0 -> nan, skipped by nanmean
+            iu_host[c] = q;
+        }
+    }
+    out_host[0] = np_nanmean(iu_host, n_cl);
+    out_host[1] = per_class ? nan("") : np_nanmean(iu_host + 1, n_cl - 1);
+    volatile double acc = correct / labeled;
+    out_host[2] = acc;
+    return MSS_OK;
 }

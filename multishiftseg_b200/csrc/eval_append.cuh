@@ -1,7 +1,11 @@
-// Device-side append of (key, label) pairs of VALID pixels to the streaming evaluator.
+// Device-side append of the order-preserving keys of VALID pixels to the streaming evaluator.
 // Replaces the host accumulation of the reference tester loop (test_deeplab.py:94-101:
 // .cpu().numpy() per batch + np.concatenate) and the label selection of metric.py:171-172.
-// Order inside the evaluator buffer is unspecified (the metric only depends on the multiset).
+//
+// Two key-only streams in one buffer (round 2; round 1 stored (key, u8 label) pairs): label == id_in keys are
+// appended upwards from keys[0], label == id_out keys downwards from keys[capacity - 1].  The label is the
+// stream, so the sort, the multi-GPU exchange and the counting pass move 4 bytes per valid pixel and never a
+// 1-byte store.  Order inside a stream is unspecified (the metric only depends on the two multisets).
 #pragma once
 #include "common.cuh"
 
@@ -9,7 +13,6 @@ namespace mss {
 
 struct EvalDev {
     uint32_t *keys;
-    uint8_t *labs;
     EvalState *state;
     long long capacity;
 };
@@ -48,27 +51,23 @@ __device__ __forceinline__ unsigned classify4(const void *labels, int dtype, lon
     return m;
 }
 
-// CTA-aggregated append in two halves, so that the one global atomic per CTA (a ~0.5 us round trip to L2) overlaps the
-// scoring arithmetic instead of sitting between two barriers: with ~100 registers per thread only two scoring CTAs fit on
-// an SM, and the serial form (score, barrier, atomic, barrier, write) left the fused kernel at 81 % of the HBM roofline
-// against 97 % for scoring alone.
-//   block_reserve4  labels only: classify, count, ONE atomicAdd per CTA reserves the output range; thread 0 keeps the
-//                   returned base in a register and nobody waits for it yet
-//   block_commit4   after the scores exist: publish the base, write (key, label) pairs
+// CTA-aggregated append in two halves, so that the global atomics (one per stream and CTA, a ~0.5 us round trip to
+// L2) overlap the scoring arithmetic instead of sitting between two barriers:
+//   block_reserve4  labels only: classify, count, ONE atomicAdd per stream and CTA reserves the output ranges;
+//                   thread 0 keeps the returned bases in registers and nobody waits for them yet
+//   block_commit4   after the scores exist: publish the bases, write the keys
 // Every thread of the CTA must call both (they contain __syncthreads).
-// (Measured, round 1, cfg-4 scoring+append: serial form 68.1 ms, this split 65.6 ms; additionally compacting each warp's
-// pairs in shared memory so that consecutive lanes store consecutive elements: 66.3 ms -- not kept.)
+// Counts travel packed: negatives in the low 16 bits, positives in the high 16 (a CTA holds <= 4 * BLOCK pixels).
 struct AppendTicket {
-    unsigned cnt, inc;             // this thread's valid pixels, inclusive warp scan of them
-    unsigned tot;                  // thread 0: valid pixels of the CTA
-    unsigned long long base;       // thread 0: reserved offset (atomic result, possibly still in flight)
+    unsigned cnt, inc;             // this thread's (neg | pos << 16) counts, inclusive warp scan of them
+    unsigned tot;                  // thread 0: counts of the CTA
+    unsigned long long base_neg, base_pos;   // thread 0: reserved offsets (atomic results, possibly still in flight)
 };
 
 template <int BLOCK>
 struct AppendSmem {
     unsigned warp_cnt[BLOCK / 32];
-    unsigned warp_pos[BLOCK / 32];
-    unsigned long long cta_base;
+    unsigned long long cta_base[2];
 };
 template <int BLOCK>
 __device__ __forceinline__ AppendSmem<BLOCK> &append_smem() {
@@ -78,14 +77,14 @@ __device__ __forceinline__ AppendSmem<BLOCK> &append_smem() {
 
 template <int BLOCK>
 __device__ __forceinline__ AppendTicket block_reserve4(unsigned mask, const EvalDev &ev) {
+    static_assert(BLOCK * 4 < 65536, "packed 16-bit counts");
     AppendSmem<BLOCK> &sm = append_smem<BLOCK>();
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     AppendTicket t;
-    t.cnt = __popc(mask & 15u);
-    t.tot = 0;
-    t.base = 0;
     const unsigned pos = __popc(mask >> 4);
-    // warp inclusive scan of cnt, warp sum of pos
+    t.cnt = (__popc(mask & 15u) - pos) | (pos << 16);
+    t.tot = 0;
+    t.base_neg = t.base_pos = 0;
     unsigned inc = t.cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -93,23 +92,19 @@ __device__ __forceinline__ AppendTicket block_reserve4(unsigned mask, const Eval
         if (lane >= d) inc += u;
     }
     t.inc = inc;
-    const unsigned psum = __reduce_add_sync(0xffffffffu, pos);
-    if (lane == 31) { sm.warp_cnt[warp] = inc; sm.warp_pos[warp] = psum; }
+    if (lane == 31) sm.warp_cnt[warp] = inc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned tot = 0, ptot = 0;
+        unsigned tot = 0;
 #pragma unroll
         for (int w = 0; w < BLOCK / 32; w++) {
             unsigned c = sm.warp_cnt[w];
             sm.warp_cnt[w] = tot;       // exclusive warp offsets (read by the other threads after commit's barrier)
             tot += c;
-            ptot += sm.warp_pos[w];
         }
         t.tot = tot;
-        if (tot) {
-            t.base = atomicAdd(&ev.state->count, (unsigned long long)tot);
-            if (ptot) atomicAdd(&ev.state->n_pos, (unsigned long long)ptot);
-        }
+        if (tot & 0xffffu) t.base_neg = atomicAdd(&ev.state->n_neg, (unsigned long long)(tot & 0xffffu));
+        if (tot >> 16) t.base_pos = atomicAdd(&ev.state->n_pos, (unsigned long long)(tot >> 16));
     }
     return t;
 }
@@ -134,23 +129,29 @@ __device__ __forceinline__ void block_commit4(const float s[4], unsigned mask, c
     if (bad & 2u) atomicOr(&ev.state->inf_flag, 1u);
 
     if (threadIdx.x == 0) {
-        unsigned long long base = t.base;
-        if (t.tot && base + t.tot > (unsigned long long)ev.capacity) {
-            atomicAdd(&ev.state->overflow, (unsigned long long)t.tot);
-            base = ~0ull;        // drop: host reports MSS_ERR_WORKSPACE
+        // each stream is kept inside the buffer here (memory safety); the two streams meeting in the middle
+        // (n_neg + n_pos > capacity) is detected when the state is read (mss_eval_state_host)
+        unsigned long long bn = t.base_neg, bp = t.base_pos;
+        const unsigned tn = t.tot & 0xffffu, tp = t.tot >> 16;
+        if ((tn && bn + tn > (unsigned long long)ev.capacity) || (tp && bp + tp > (unsigned long long)ev.capacity)) {
+            atomicAdd(&ev.state->overflow, (unsigned long long)(tn + tp));
+            bn = bp = ~0ull;        // drop: host reports MSS_ERR_WORKSPACE
         }
-        sm.cta_base = base;
+        sm.cta_base[0] = bn;
+        sm.cta_base[1] = bp;
     }
     __syncthreads();
-    const unsigned long long base = sm.cta_base;
-    if (base != ~0ull && t.cnt) {
-        unsigned long long o = base + sm.warp_cnt[warp] + (t.inc - t.cnt);
+    const unsigned long long bn = sm.cta_base[0];
+    if (bn != ~0ull && t.cnt) {
+        const unsigned ex = sm.warp_cnt[warp] + (t.inc - t.cnt);       // packed exclusive offsets inside the CTA
+        unsigned long long on = bn + (ex & 0xffffu);
+        unsigned long long op = (unsigned long long)ev.capacity - 1 - (sm.cta_base[1] + (ex >> 16));
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if ((mask >> j) & 1u) {
-                ev.keys[o] = score_key_desc(s[j]);
-                ev.labs[o] = (uint8_t)((mask >> (4 + j)) & 1u);
-                o++;
+                const uint32_t k = score_key_desc(s[j]);
+                if ((mask >> (4 + j)) & 1u) ev.keys[op--] = k;
+                else ev.keys[on++] = k;
             }
         }
     }

@@ -444,13 +444,12 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
             if (use_tc5q) {
                 // debug switch: MSS_M2F_DUP_B=1 keeps two copies of each class-table core matrix instead of LBO = 0
                 static const bool dup_b = [] { const char *e = getenv("MSS_M2F_DUP_B"); return e && e[0] == '1'; }();
-                static std::atomic<bool> tq_attr_set{false};
-                if (!tq_attr_set.load()) {
+                static std::atomic<unsigned long long> tq_attr_set{0};
+                if (first_use_on_device(tq_attr_set)) {
                     MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tq_smem(false)));
                     MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tq_smem(false)));
                     MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tq_smem(true)));
                     MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5q_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tq_smem(true)));
-                    tq_attr_set.store(true);
                 }
                 // blocks of 4 pixels start at x = 2 (mod 4): CTA bx covers x in [64 bx - 2, 64 bx + 62)
                 dim3 grid((Wc + 2 + TQ_W - 1) / TQ_W, (Hc + TQ_H - 1) / TQ_H, (unsigned)B);
@@ -465,11 +464,10 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
                 MSS_CHECK_LAUNCH();
                 return MSS_OK;
             }
-            static std::atomic<bool> tc5_attr_set{false};
-            if (!tc5_attr_set.load()) {
+            static std::atomic<unsigned long long> tc5_attr_set{0};
+            if (first_use_on_device(tc5_attr_set)) {
                 MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5_x4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM));
                 MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_tc5_x4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM));
-                tc5_attr_set.store(true);
             }
             dim3 grid((Wc + T5_TILE_W - 1) / T5_TILE_W, (Hc + T5_BLOCK_H - 1) / T5_BLOCK_H, (unsigned)B);
             MSS_REQUIRE(grid.y <= 65535, "mss_m2f_semantic_inference: grid too large");
@@ -485,10 +483,9 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
                                                                                               p_hi, p_lo);
             MSS_CHECK_LAUNCH();
             const size_t smem = (size_t)MM_PATCH_BYTES + 2 * (size_t)MM_QPAD * MM_NPAD * 4 + MM_QPAD * 8 + 8 + 128;
-            static std::atomic<bool> mma_attr_set{false};
-            if (!mma_attr_set.load()) {
+            static std::atomic<unsigned long long> mma_attr_set{0};
+            if (first_use_on_device(mma_attr_set)) {
                 MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_mma_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                mma_attr_set.store(true);
             }
             dim3 grid((Wc + MM_TILE_W - 1) / MM_TILE_W, (Hc + MM_TILE_H - 1) / MM_TILE_H, (unsigned)B);
             MSS_REQUIRE(grid.y <= 65535, "mss_m2f_semantic_inference: grid too large");
@@ -497,10 +494,9 @@ extern "C" int mss_m2f_semantic_inference(const float *cls_logits, const float *
             return MSS_OK;
         }
         const size_t smem = (size_t)STAGES * STAGE_BYTES + (size_t)M2F_MAXQ * M2F_CP * 4 + M2F_MAXQ * 8 + STAGES * 8 + 128;
-        static std::atomic<bool> attr_set{false};
-        if (!attr_set.load()) {
+        static std::atomic<unsigned long long> attr_set{0};
+        if (first_use_on_device(attr_set)) {
             MSS_CHECK_CUDA(cudaFuncSetAttribute(m2f_fused_x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set.store(true);
         }
         dim3 grid((Wc + TILE_W - 1) / TILE_W, (Hc + TILE_H - 1) / TILE_H, (unsigned)B);
         m2f_fused_x4_kernel<<<grid, 256, smem, st>>>(tmap, probs, Q, h, w, out);

@@ -1,9 +1,13 @@
-// (a9-a13) exact tie-aware AUROC / AP / FPR@95TPR from sorted (key, label) pairs.
+// (a9-a13) exact tie-aware AUROC / AP / FPR@95TPR from the two sorted key streams of an evaluation
+// (negatives = in-distribution keys, positives = OOD keys; ascending key == descending float32 score).
 //
 // Integer stage (bit-exact by construction):
-//   thresholds = ends of runs of equal keys (== np.where(np.diff(y_score)) + last index,
-//   sklearn _ranking.py:916-920, metric.py:110-111);  tps[k] = #positives at positions <= end_k
-//   (cumsum(y)[idx], _ranking.py:1034 / metric.py:114), fps[k] = 1 + end_k - tps[k].
+//   thresholds = distinct keys of the merged streams (== np.where(np.diff(y_score)) + last index,
+//   sklearn _ranking.py:916-920, metric.py:110-111);  tps[k] = #positives with key <= threshold k
+//   (cumsum(y)[idx], _ranking.py:1034 / metric.py:114), fps[k] = #negatives with key <= threshold k
+//   (= 1 + idx - tps).  One merge-path pass over both streams, one decoupled look-back for the compaction
+//   offset: every key is read once, every threshold written once (round 1: a count pass, a single-CTA scan
+//   and a write pass over (key, label) pairs).
 // float64 tail (must reproduce numpy/sklearn rounding exactly, so: explicit __d*_rn intrinsics, no
 // FMA contraction, and numpy's pairwise summation tree replayed leaf by leaf):
 //   AUROC  roc_curve(drop_intermediate=True) + auc/trapezoid   _ranking.py:1331-1378, :53-116
@@ -13,7 +17,7 @@
 #include <map>
 #include <vector>
 
-#include "common.cuh"
+#include "sort_plan.cuh"
 
 namespace mss {
 
@@ -21,143 +25,144 @@ constexpr int CT_THREADS = 256;
 constexpr int CT_IPT = 8;
 constexpr int CT_TILE = CT_THREADS * CT_IPT;  // 2048
 
-struct Pair64 {
-    unsigned long long a, b;
-};
-
-// block-wide exclusive scan of one (a, b) pair per thread; returns exclusive prefix, total in `tot`
-__device__ __forceinline__ uint2 block_exclusive_scan2(uint2 v, uint2 &tot) {
-    __shared__ uint2 s_w[CT_THREADS / 32];
+// block-wide exclusive scan of one count per thread; CTA total in `tot`
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned &tot) {
+    __shared__ unsigned s_w[CT_THREADS / 32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint2 inc = v;
+    unsigned inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        unsigned ta = __shfl_up_sync(0xffffffffu, inc.x, d), tb = __shfl_up_sync(0xffffffffu, inc.y, d);
-        if (lane >= d) { inc.x += ta; inc.y += tb; }
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
     }
     if (lane == 31) s_w[warp] = inc;
     __syncthreads();
-    uint2 base = make_uint2(0, 0), all = make_uint2(0, 0);
+    unsigned base = 0, all = 0;
 #pragma unroll
     for (int w = 0; w < CT_THREADS / 32; w++) {
-        uint2 x = s_w[w];
-        if (w < (int)warp) { base.x += x.x; base.y += x.y; }
-        all.x += x.x; all.y += x.y;
+        const unsigned x = s_w[w];
+        if (w < (int)warp) base += x;
+        all += x;
     }
     tot = all;
     __syncthreads();
-    return make_uint2(base.x + inc.x - v.x, base.y + inc.y - v.y);
+    return base + inc - v;
 }
 
-// ---- sorted pairs -> (tps, fps) ---------------------------------------------------------------------
-// phase A (SCATTER=false): per-tile (#run ends, #positives).  phase C (SCATTER=true): write counts.
-template <bool SCATTER>
+// ---- sorted streams -> (tps, fps) -----------------------------------------------------------------
+// Merge path: among the first `diag` keys of the merged order (ties: negatives first -- the order inside a tie
+// does not matter, a threshold is emitted at the END of a run of equal keys), how many come from A?
+__device__ __forceinline__ long long merge_path(const uint32_t *__restrict__ A, long long nA,
+                                                const uint32_t *__restrict__ B, long long nB, long long diag) {
+    long long lo = diag > nB ? diag - nB : 0, hi = diag < nA ? diag : nA;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(A + mid) <= __ldg(B + (diag - 1 - mid))) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// one thread per tile boundary: a_start[t] = merge path at diagonal min(t * CT_TILE, nA + nB), t = 0 .. tiles_upper
+__global__ void __launch_bounds__(256)
+merge_partition_kernel(const SortPlan *__restrict__ plan, long long *__restrict__ a_start, long long tiles_upper) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > tiles_upper) return;
+    const long long nA = plan->seg[0].n, nB = plan->seg[1].n;
+    const long long diag = min(t * CT_TILE, nA + nB);
+    a_start[t] = merge_path(plan->seg[0].x, nA, plan->seg[1].x, nB, diag);
+}
+
+// totals[0] = T (distinct keys), written by the last tile
 __global__ void __launch_bounds__(CT_THREADS)
-runs_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restrict__ labs, long long n,
-            uint2 *__restrict__ tile_sums, const Pair64 *__restrict__ tile_excl, long long pos_before,
-            long long idx_before, long long *__restrict__ tps, long long *__restrict__ fps) {
-    const long long tile0 = (long long)blockIdx.x * CT_TILE;
-    const long long i0 = tile0 + (long long)threadIdx.x * CT_IPT;
-    uint32_t k[CT_IPT + 1];
-    uint8_t l[CT_IPT];
-    static_assert(CT_IPT == 8, "vector path below loads 2 x uint4 keys + 1 x uint2 labels");
-    if (i0 + CT_IPT <= n && (((uintptr_t)keys & 15) | ((uintptr_t)labs & 7)) == 0) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(keys + i0));
-        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(keys + i0 + 4));
-        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(labs + i0));
-        k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            l[j] = (uint8_t)(v.x >> (8 * j));
-            l[4 + j] = (uint8_t)(v.y >> (8 * j));
-        }
-    } else {
+merge_counts_kernel(const SortPlan *__restrict__ plan, const long long *__restrict__ a_start, long long pos_before,
+                    long long neg_before, long long *__restrict__ tps, long long *__restrict__ fps,
+                    unsigned long long *status, unsigned *counter, unsigned long long *__restrict__ totals) {
+    __shared__ uint32_t s_k[CT_TILE];
+    __shared__ long long s_t[CT_TILE], s_f[CT_TILE];
+    __shared__ unsigned s_tile;
+    __shared__ unsigned long long s_excl;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);       // tiles in start order: the look-back never waits on a tile not yet running
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const uint32_t *__restrict__ A = plan->seg[0].x, *__restrict__ B = plan->seg[1].x;
+    const long long nA = plan->seg[0].n, nB = plan->seg[1].n, M = nA + nB;
+    const long long tiles = (M + CT_TILE - 1) / CT_TILE;
+    if ((long long)tile >= tiles) return;
+    const long long d0 = (long long)tile * CT_TILE, d1 = min(M, d0 + CT_TILE);
+    const long long a0 = a_start[tile], a1 = a_start[tile + 1], b0 = d0 - a0, b1 = d1 - a1;
+    const int na = (int)(a1 - a0), nb = (int)(b1 - b0), cnt = na + nb;
+    for (int i = tid; i < cnt; i += CT_THREADS) s_k[i] = (i < na) ? __ldg(A + a0 + i) : __ldg(B + b0 + (i - na));
+    // the key that follows this tile in the merged order (decides whether the tile's last key ends a run)
+    const bool has_next = d1 < M;
+    uint32_t nxt = 0;
+    if (has_next) {
+        const uint32_t ka = (a1 < nA) ? __ldg(A + a1) : 0xFFFFFFFFu, kb = (b1 < nB) ? __ldg(B + b1) : 0xFFFFFFFFu;
+        nxt = (a1 < nA && b1 < nB) ? min(ka, kb) : (a1 < nA ? ka : kb);
+    }
+    __syncthreads();
+
+    // this thread's CT_IPT keys of the merged order start at diagonal `diag` of the tile
+    const int diag = min((int)tid * CT_IPT, cnt);
+    int lo = max(0, diag - nb), hi = min(diag, na);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_k[mid] <= s_k[na + diag - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    int ai = lo, bi = diag - lo;
+    const int ai0 = ai;
+    unsigned took_a = 0, ends = 0, n_end = 0;
+    {
+        bool ta = (bi >= nb) || (ai < na && s_k[ai] <= s_k[na + bi]);
+        uint32_t key = (diag < cnt) ? (ta ? s_k[ai] : s_k[na + bi]) : 0u;
 #pragma unroll
         for (int j = 0; j < CT_IPT; j++) {
-            k[j] = (i0 + j < n) ? __ldg(keys + i0 + j) : 0u;
-            l[j] = (i0 + j < n) ? __ldg(labs + i0 + j) : (uint8_t)0;
-        }
-    }
-    k[CT_IPT] = (i0 + CT_IPT < n) ? __ldg(keys + i0 + CT_IPT) : 0u;
-    unsigned ends = 0, npos = 0;
-#pragma unroll
-    for (int j = 0; j < CT_IPT; j++) {
-        const long long i = i0 + j;
-        if (i < n) {
-            const bool end = (i == n - 1) || (k[j] != k[j + 1]);
-            ends += end;
-            npos += l[j];
-        }
-    }
-    uint2 tot;
-    uint2 ex = block_exclusive_scan2(make_uint2(ends, npos), tot);
-    if (!SCATTER) {
-        if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
-        return;
-    }
-    // stage the tile's thresholds in shared memory (thread-order == output order), then write them out coalesced
-    __shared__ long long s_t[CT_TILE], s_f[CT_TILE];
-    const Pair64 te = tile_excl[blockIdx.x];
-    unsigned slot = ex.x;
-    unsigned long long cp = te.b + ex.y;
-#pragma unroll
-    for (int j = 0; j < CT_IPT; j++) {
-        const long long i = i0 + j;
-        if (i < n) {
-            cp += l[j];
-            const bool end = (i == n - 1) || (k[j] != k[j + 1]);
-            if (end) {
-                const long long t = pos_before + (long long)cp;
-                s_t[slot] = t;
-                s_f[slot] = idx_before + i + 1 - t;
-                slot++;
+            const int p = diag + j;
+            if (p < cnt) {
+                if (ta) { ai++; took_a |= 1u << j; } else bi++;
+                bool end;
+                if (p + 1 < cnt) {
+                    ta = (bi >= nb) || (ai < na && s_k[ai] <= s_k[na + bi]);
+                    const uint32_t nk = ta ? s_k[ai] : s_k[na + bi];
+                    end = nk != key;
+                    key = nk;
+                } else {
+                    end = !has_next || nxt != key;
+                }
+                if (end) { ends |= 1u << j; n_end++; }
             }
         }
     }
-    __syncthreads();
-    for (unsigned q = threadIdx.x; q < tot.x; q += CT_THREADS) {
-        tps[te.a + q] = s_t[q];
-        fps[te.a + q] = s_f[q];
-    }
-}
-
-// exclusive scan of per-tile (a, b) sums by ONE block (tiles <= a few million); totals -> out[0..1]
-__global__ void __launch_bounds__(1024)
-tile_scan_kernel(const uint2 *__restrict__ sums, long long tiles, Pair64 *__restrict__ excl,
-                 unsigned long long *__restrict__ totals) {
-    __shared__ unsigned long long s_a[32], s_b[32];
-    __shared__ unsigned long long s_carry[2];
-    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = 0; base < tiles; base += 1024) {
-        const long long t = base + threadIdx.x;
-        uint2 v = (t < tiles) ? sums[t] : make_uint2(0, 0);
-        unsigned long long a = v.x, b = v.y, ia = a, ib = b;
+    unsigned tot;
+    unsigned slot = block_exclusive_scan(n_end, tot);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned long long ta = __shfl_up_sync(0xffffffffu, ia, d), tb = __shfl_up_sync(0xffffffffu, ib, d);
-            if (lane >= d) { ia += ta; ib += tb; }
+    for (int j = 0; j < CT_IPT; j++) {
+        if ((ends >> j) & 1u) {
+            const int aj = ai0 + __popc(took_a & ((2u << j) - 1u));      // negatives consumed up to and including item j
+            const int bj = diag + j + 1 - aj;
+            s_t[slot] = pos_before + b0 + bj;
+            s_f[slot] = neg_before + a0 + aj;
+            slot++;
         }
-        if (lane == 31) { s_a[warp] = ia; s_b[warp] = ib; }
-        __syncthreads();
-        unsigned long long wa = 0, wb = 0, alla = 0, allb = 0;
-        for (int w = 0; w < 32; w++) {
-            if (w < (int)warp) { wa += s_a[w]; wb += s_b[w]; }
-            alla += s_a[w]; allb += s_b[w];
-        }
-        const unsigned long long ca = s_carry[0], cb = s_carry[1];
-        if (t < tiles) { excl[t].a = ca + wa + ia - a; excl[t].b = cb + wb + ib - b; }
-        __syncthreads();
-        if (threadIdx.x == 0) { s_carry[0] = ca + alla; s_carry[1] = cb + allb; }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) { totals[0] = s_carry[0]; totals[1] = s_carry[1]; }
+    if (tid < 32) {
+        const unsigned long long ex = warp_lookback(status, tile, tot);
+        if (tid == 0) {
+            s_excl = ex;
+            if ((long long)tile == tiles - 1) totals[0] = ex + tot;
+        }
+    }
+    __syncthreads();
+    const unsigned long long ex = s_excl;
+    for (unsigned q = tid; q < tot; q += CT_THREADS) {
+        tps[ex + q] = s_t[q];
+        fps[ex + q] = s_f[q];
+    }
 }
 
 // ---- ROC: drop collinear points (roc_curve drop_intermediate, _ranking.py:1338-1350) ----------------
 // ---- FPR@95: argmin_k |tps[k]/P - 0.95| over k <= first k with tps[k]==P, ties -> largest k -----------
-//      (fpr_and_fdr_at_recall, metric.py:116-127; fused into the counting pass below: same data window)
+//      (fpr_and_fdr_at_recall, metric.py:116-127; fused into the compaction pass below: same data window)
 struct Best {
     double d;
     long long k;
@@ -180,16 +185,28 @@ __device__ __forceinline__ Best block_best(Best b) {      // valid in thread 0
     return b;
 }
 
-// One thread owns thresholds [i0, i0+8); it needs (tps, fps) at i0-1 .. i0+8: 10 + 10 loads instead of the
-// 48 a per-point second difference would issue.  SCATTER=false: per-tile kept count (+ the FPR95 candidate
-// of the tile); SCATTER=true: write the kept points.
-template <bool SCATTER>
+// T comes from the device (totals of the counting pass) when d_T is given, else from the host.
+__device__ __forceinline__ long long load_T(const unsigned long long *d_T, long long T_host) {
+    return d_T ? (long long)*d_T : T_host;
+}
+
+// Single pass: one thread owns thresholds [i0, i0+8) and needs (tps, fps) at i0-1 .. i0+8; kept points are written
+// at the offset a decoupled look-back delivers; the FPR95 candidate of the tile goes to tile_best[tile].
+// totals_out[0] = number of kept points (written by the last tile).
 __global__ void __launch_bounds__(CT_THREADS)
-roc_compact_kernel(const long long *__restrict__ tps, const long long *__restrict__ fps, long long T,
-                   double recall_level, uint2 *__restrict__ tile_sums, Best *__restrict__ tile_best,
-                   const Pair64 *__restrict__ tile_excl, long long *__restrict__ tps_k,
-                   long long *__restrict__ fps_k) {
-    const long long i0 = (long long)blockIdx.x * CT_TILE + (long long)threadIdx.x * CT_IPT;
+roc_compact_kernel(const long long *__restrict__ tps, const long long *__restrict__ fps, const unsigned long long *d_T,
+                   long long T_host, double recall_level, unsigned long long *status, unsigned *counter,
+                   Best *__restrict__ tile_best, long long *__restrict__ tps_k, long long *__restrict__ fps_k,
+                   unsigned long long *__restrict__ totals_out) {
+    __shared__ unsigned s_tile;
+    __shared__ unsigned long long s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const long long T = load_T(d_T, T_host);
+    const long long tiles = (T + CT_TILE - 1) / CT_TILE;
+    if ((long long)tile >= tiles) return;
+    const long long i0 = (long long)tile * CT_TILE + (long long)threadIdx.x * CT_IPT;
     long long t[CT_IPT + 2], f[CT_IPT + 2];                  // window index w <-> threshold i0 - 1 + w
     if (i0 + CT_IPT <= T && ((((uintptr_t)tps) | ((uintptr_t)fps)) & 15) == 0) {
 #pragma unroll
@@ -226,11 +243,10 @@ roc_compact_kernel(const long long *__restrict__ tps, const long long *__restric
             if (kp) { keep |= 1u << j; cnt++; }
         }
     }
-    uint2 tot;
-    uint2 ex = block_exclusive_scan2(make_uint2(cnt, 0), tot);
-    if (!SCATTER) {
-        if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
-        // FPR95 candidate of this tile
+    unsigned tot;
+    const unsigned ex = block_exclusive_scan(cnt, tot);
+    // FPR95 candidate of this tile
+    {
         const double P = (double)__ldg(tps + T - 1);
         Best b{INFINITY, -1};
 #pragma unroll
@@ -242,10 +258,17 @@ roc_compact_kernel(const long long *__restrict__ tps, const long long *__restric
             }
         }
         b = block_best(b);
-        if (threadIdx.x == 0) tile_best[blockIdx.x] = b;
-        return;
+        if (threadIdx.x == 0) tile_best[tile] = b;
     }
-    unsigned long long o = tile_excl[blockIdx.x].a + ex.x;
+    if (threadIdx.x < 32) {
+        const unsigned long long e = warp_lookback(status, tile, tot);
+        if (threadIdx.x == 0) {
+            s_excl = e;
+            if ((long long)tile == tiles - 1) totals_out[0] = e + tot;
+        }
+    }
+    __syncthreads();
+    unsigned long long o = s_excl + ex;
 #pragma unroll
     for (int j = 0; j < CT_IPT; j++) {
         if ((keep >> j) & 1u) {
@@ -256,9 +279,10 @@ roc_compact_kernel(const long long *__restrict__ tps, const long long *__restric
     }
 }
 
-// reduce n candidates to gridDim.x candidates (grid-stride)
+// reduce the tile candidates to gridDim.x candidates (grid-stride)
 __global__ void __launch_bounds__(CT_THREADS)
-fpr_reduce_kernel(const Best *__restrict__ in, long long n, Best *__restrict__ out) {
+fpr_reduce_kernel(const Best *__restrict__ in, const unsigned long long *d_T, long long T_host, Best *__restrict__ out) {
+    const long long T = load_T(d_T, T_host), n = (T + CT_TILE - 1) / CT_TILE;
     Best b{INFINITY, -1};
     for (long long i = (long long)blockIdx.x * CT_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * CT_THREADS)
         b = better(b, in[i]);
@@ -266,16 +290,18 @@ fpr_reduce_kernel(const Best *__restrict__ in, long long n, Best *__restrict__ o
     if (threadIdx.x == 0) out[blockIdx.x] = b;
 }
 
+// n_partial > 0: `cand` holds n_partial reduced candidates; else it holds one candidate per tile
 __global__ void __launch_bounds__(CT_THREADS)
-fpr_final_kernel(const Best *__restrict__ partial, int n, const long long *__restrict__ fps, long long T,
-                 double *__restrict__ out, long long *__restrict__ kout) {
-    const double N = (double)fps[T - 1];
+fpr_final_kernel(const Best *__restrict__ cand, int n_partial, const long long *__restrict__ fps,
+                 const unsigned long long *d_T, long long T_host, double *__restrict__ out) {
+    const long long T = load_T(d_T, T_host);
+    const long long n = n_partial > 0 ? n_partial : (T + CT_TILE - 1) / CT_TILE;
     Best b{INFINITY, -1};
-    for (int i = threadIdx.x; i < n; i += CT_THREADS) b = better(b, partial[i]);
+    for (long long i = threadIdx.x; i < n; i += CT_THREADS) b = better(b, cand[i]);
     b = block_best(b);
     if (threadIdx.x == 0) {
+        const double N = T > 0 ? (double)fps[T - 1] : 0.0;
         out[0] = (b.k >= 0) ? __ddiv_rn((double)fps[b.k], N) : nan("");   // k < 0 only when P == 0 (caller reports it)
-        kout[0] = b.k;
     }
 }
 
@@ -351,21 +377,25 @@ struct PwTree {
     }
 };
 
-// one thread per leaf: start offsets of all leaves (leaf_start[n_leaves] = n)
+// one thread per leaf: start offsets of all leaves (leaf_start[n_leaves] = n); blockIdx.y selects the tree (AP / ROC)
+struct PwTree2 {
+    PwTree tree[2];
+    long long *leaf_start[2];
+};
 __global__ void __launch_bounds__(256)
-leaf_bounds_kernel(PwTree tree, long long *__restrict__ leaf_start) {
+leaf_bounds_kernel(PwTree2 tt) {
+    const PwTree &tree = tt.tree[blockIdx.y];
     const long long leaf = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf > tree.n_leaves) return;
     long long s = tree.n, m = 0;
     if (leaf < tree.n_leaves) tree.leaf_bounds(leaf, s, m);
-    leaf_start[leaf] = s;
+    tt.leaf_start[blockIdx.y][leaf] = s;
 }
 
 // 8 lanes per leaf = numpy's 8 interleaved accumulators
 template <typename Term>
-__global__ void __launch_bounds__(256)
-leaf_sum_kernel(Term term, const long long *__restrict__ leaf_start, long long n_leaves,
-                double *__restrict__ leaf_sum) {
+__device__ __forceinline__ void leaf_sum_body(const Term &term, const long long *__restrict__ leaf_start, long long n_leaves,
+                                              double *__restrict__ leaf_sum) {
     const long long leaf = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const unsigned sub = threadIdx.x & 7;
     const bool live = leaf < n_leaves;
@@ -390,6 +420,25 @@ leaf_sum_kernel(Term term, const long long *__restrict__ leaf_start, long long n
             for (long long i = body; i < m; i++) res = __dadd_rn(res, term(s + i));
     }
     if (live && sub == 0) leaf_sum[leaf] = res;
+}
+
+// blockIdx.y = 0: AP leaves, 1: ROC leaves (one launch for both sums)
+struct LeafJob {
+    ApTerm ap;
+    RocTerm roc;
+    const long long *leaf_start[2];
+    long long n_leaves[2];
+    double *leaf_sum[2];
+};
+__global__ void __launch_bounds__(256)
+leaf_sum_kernel(LeafJob job) {
+    if (blockIdx.y == 0) {
+        if ((long long)blockIdx.x * 32 >= job.n_leaves[0]) return;
+        leaf_sum_body(job.ap, job.leaf_start[0], job.n_leaves[0], job.leaf_sum[0]);
+    } else {
+        if ((long long)blockIdx.x * 32 >= job.n_leaves[1]) return;
+        leaf_sum_body(job.roc, job.leaf_start[1], job.n_leaves[1], job.leaf_sum[1]);
+    }
 }
 
 // The tree above the leaves.  The host cuts it at "frontier" nodes (the first node on each root path
@@ -438,12 +487,18 @@ __host__ __device__ inline double pw_subtree_combine(long long m, const double *
     }
 }
 
+struct CombineJob {
+    const PwFrontNode *nodes[2];
+    int n_nodes[2];
+    const double *leaf_sum[2];
+    double *node_sum[2];
+};
 __global__ void __launch_bounds__(128)
-subtree_combine_kernel(const PwFrontNode *__restrict__ nodes, int n_nodes, const double *__restrict__ leaf_sum,
-                       double *__restrict__ node_sum) {
+subtree_combine_kernel(CombineJob job) {
+    const int y = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    node_sum[i] = pw_subtree_combine(nodes[i].m, leaf_sum, nodes[i].first_leaf);
+    if (i >= job.n_nodes[y]) return;
+    job.node_sum[y][i] = pw_subtree_combine(job.nodes[y][i].m, job.leaf_sum[y], job.nodes[y][i].first_leaf);
 }
 
 // ---- host side of the pairwise tree ----------------------------------------------------------------
@@ -508,185 +563,240 @@ struct PwDevice {
 
 static size_t ct_tiles(int64_t n) { return (size_t)((n + CT_TILE - 1) / CT_TILE); }
 
+// ---- counting stage ----------------------------------------------------------------------------------
+struct CountsWs {
+    SortPlan *plan;                // used when the caller has no plan of its own (mss_counts_from_sorted)
+    long long *a_start;            // [tiles_upper + 1] merge-path splits at the tile boundaries
+    unsigned *counter;             // tile ticket           } zeroed together
+    unsigned long long *totals;    // [0] = T               }
+    unsigned long long *status;    // [tiles_upper]         }
+    char *zero_base;
+    size_t zero_bytes, tiles_upper;
+};
+static bool carve_counts(void *ws, size_t bytes, int64_t n_upper, CountsWs &o) {
+    Carver c(ws, bytes);
+    o.tiles_upper = ct_tiles(n_upper);
+    o.plan = c.take<SortPlan>(1);
+    o.a_start = c.take<long long>(o.tiles_upper + 1);
+    o.counter = c.take<unsigned>(64);
+    o.zero_base = (char *)o.counter;
+    o.totals = c.take<unsigned long long>(4);
+    o.status = c.take<unsigned long long>(o.tiles_upper + 1);
+    o.zero_bytes = (size_t)((char *)(o.status + o.tiles_upper + 1) - o.zero_base);
+    return c.ok();
+}
+static size_t counts_ws_bytes(int64_t n) {
+    if (n < 0) n = 0;
+    return 256 + align_up((ct_tiles(n) + 1) * 8, 256) + 256 + 256 + align_up((ct_tiles(n) + 1) * 8, 256) + 1024;
+}
+
+// merge the plan's two sorted streams into per-threshold cumulative counts; T lands in w.totals[0] (device)
+static int counts_enqueue(const SortPlan *plan, int64_t n_upper, int64_t pos_before, int64_t neg_before, int64_t *tps,
+                          int64_t *fps, const CountsWs &w, cudaStream_t st) {
+    MSS_REQUIRE(w.tiles_upper < (1ull << 31), "counts: n too large");
+    MSS_CHECK_CUDA(cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, st));
+    if (w.tiles_upper == 0) return MSS_OK;
+    merge_partition_kernel<<<(unsigned)((w.tiles_upper + 1 + 255) / 256), 256, 0, st>>>(plan, w.a_start, (long long)w.tiles_upper);
+    MSS_CHECK_LAUNCH();
+    merge_counts_kernel<<<(unsigned)w.tiles_upper, CT_THREADS, 0, st>>>(plan, w.a_start, pos_before, neg_before, (long long *)tps,
+                                                                       (long long *)fps, w.status, w.counter, w.totals);
+    MSS_CHECK_LAUNCH();
+    return MSS_OK;
+}
+
+// ---- float64 tail --------------------------------------------------------------------------------------
+struct TailWs {
+    long long *tps_k, *fps_k;       // [T_upper] points kept by roc_curve(drop_intermediate=True)
+    Best *tile_best, *partial;      // FPR95 candidates per tile / reduced
+    double *sum_ap, *sum_roc;       // leaf sums
+    long long *leaf_start[2];
+    char *blob;                     // tree tables + frontier nodes of both trees (one H2D copy)
+    double *results;                // [0] = FPR95, then the frontier sums of both trees (one D2H copy)
+    unsigned *counter;              // } zeroed together
+    unsigned long long *totals;     // } [0] = T_roc
+    unsigned long long *status;     // } [tiles_upper + 1]
+    char *zero_base;
+    size_t zero_bytes, tiles_upper, max_leaves;
+};
+static size_t pw_blob_bytes() { return 2 * (2 * (size_t)PW_MAX_SIZES * 8 + (size_t)PW_MAX_FRONT * sizeof(PwFrontNode)); }
+static bool carve_tail(void *ws, size_t bytes, int64_t T_upper, TailWs &o) {
+    Carver c(ws, bytes);
+    o.tiles_upper = ct_tiles(T_upper);
+    o.max_leaves = (size_t)T_upper / 64 + 2;
+    o.tps_k = c.take<long long>((size_t)T_upper);
+    o.fps_k = c.take<long long>((size_t)T_upper);
+    o.tile_best = c.take<Best>(o.tiles_upper + 1);
+    o.partial = c.take<Best>(1024);
+    o.sum_ap = c.take<double>(o.max_leaves);
+    o.sum_roc = c.take<double>(o.max_leaves);
+    o.leaf_start[0] = c.take<long long>(o.max_leaves + 1);
+    o.leaf_start[1] = c.take<long long>(o.max_leaves + 1);
+    o.blob = c.take<char>(pw_blob_bytes());
+    o.results = c.take<double>(2 * PW_MAX_FRONT + 8);
+    o.counter = c.take<unsigned>(64);
+    o.zero_base = (char *)o.counter;
+    o.totals = c.take<unsigned long long>(4);
+    o.status = c.take<unsigned long long>(o.tiles_upper + 1);
+    o.zero_bytes = (size_t)((char *)(o.status + o.tiles_upper + 1) - o.zero_base);
+    return c.ok();
+}
+static size_t tail_ws_bytes(int64_t T) {
+    if (T < 0) T = 0;
+    const size_t leaves = (size_t)T / 64 + 2, tiles = ct_tiles(T);
+    return 2 * align_up((size_t)T * 8, 256) + align_up((tiles + 1) * sizeof(Best), 256) + align_up(1024 * sizeof(Best), 256) +
+           2 * align_up(leaves * 8, 256) + 2 * align_up((leaves + 1) * 8, 256) + align_up(pw_blob_bytes(), 256) +
+           align_up((2 * PW_MAX_FRONT + 8) * 8, 256) + 256 + 256 + align_up((tiles + 1) * 8, 256) + 2048;
+}
+
+// stage 1 (no host data needed): ROC compaction + FPR95.  T is read from the device when d_T is given.
+// T_roc lands in w.totals[0], FPR95 in w.results[0].
+static int tail1_enqueue(const int64_t *tps_, const int64_t *fps_, const unsigned long long *d_T, int64_t T_host,
+                         double recall_level, const TailWs &w, cudaStream_t st) {
+    const long long *tps = (const long long *)tps_, *fps = (const long long *)fps_;
+    MSS_REQUIRE(w.tiles_upper < (1ull << 31), "tail: T too large");
+    MSS_CHECK_CUDA(cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, st));
+    if (w.tiles_upper == 0) return MSS_OK;
+    roc_compact_kernel<<<(unsigned)w.tiles_upper, CT_THREADS, 0, st>>>(tps, fps, d_T, T_host, recall_level, w.status, w.counter,
+                                                                      w.tile_best, w.tps_k, w.fps_k, w.totals);
+    MSS_CHECK_LAUNCH();
+    int n_partial = 0;
+    if (w.tiles_upper > 1024) {
+        fpr_reduce_kernel<<<256, CT_THREADS, 0, st>>>(w.tile_best, d_T, T_host, w.partial);
+        MSS_CHECK_LAUNCH();
+        n_partial = 256;
+    }
+    fpr_final_kernel<<<1, CT_THREADS, 0, st>>>(n_partial ? w.partial : w.tile_best, n_partial, fps, d_T, T_host, w.results);
+    MSS_CHECK_LAUNCH();
+    return MSS_OK;
+}
+
+// stage 2: T and T_roc are known on the host (they shape numpy's pairwise trees): leaf sums of both integrals in one
+// launch, combine below the frontier on the device and above it here.  Synchronises the stream.
+static int tail2_run(const int64_t *tps_, const int64_t *fps_, int64_t T, int64_t T_roc, const TailWs &w, cudaStream_t st,
+                     double out_host[3]) {
+    const long long *tps = (const long long *)tps_, *fps = (const long long *)fps_;
+    PwPlan p[2];
+    const long long nn[2] = {T, T_roc};
+    for (int y = 0; y < 2; y++)
+        if (!pw_plan(nn[y], p[y]) || (size_t)p[y].n_leaves > w.max_leaves) {
+            set_error("mss_metrics_tail: internal pairwise-plan bound exceeded (n=%lld)", nn[y]);
+            return MSS_ERR_WORKSPACE;
+        }
+    // blob: [ap.size | ap.leaves | roc.size | roc.leaves | ap.front | roc.front], 8-byte fields throughout
+    std::vector<char> blob;
+    size_t off_size[2], off_leaves[2], off_front[2];
+    auto put = [&](const void *src, size_t bytes) { const size_t o = blob.size(); blob.insert(blob.end(), (const char *)src, (const char *)src + bytes); return o; };
+    for (int y = 0; y < 2; y++) {
+        off_size[y] = put(p[y].size.data(), p[y].size.size() * 8);
+        off_leaves[y] = put(p[y].leaves.data(), p[y].leaves.size() * 8);
+    }
+    for (int y = 0; y < 2; y++) off_front[y] = put(p[y].front.data(), p[y].front.size() * sizeof(PwFrontNode));
+    MSS_REQUIRE(blob.size() <= pw_blob_bytes(), "mss_metrics_tail: internal blob bound");
+    MSS_CHECK_CUDA(cudaMemcpyAsync(w.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+
+    PwTree2 tt;
+    LeafJob lj;
+    CombineJob cj;
+    double *node_sum[2] = {w.results + 8, w.results + 8 + p[0].front.size()};
+    double *leaf_sum[2] = {w.sum_ap, w.sum_roc};
+    long long max_leaves = 0;
+    int max_front = 0;
+    for (int y = 0; y < 2; y++) {
+        tt.tree[y] = PwTree{(const long long *)(w.blob + off_size[y]), (const long long *)(w.blob + off_leaves[y]),
+                            (int)p[y].size.size(), p[y].n, p[y].n_leaves};
+        tt.leaf_start[y] = w.leaf_start[y];
+        lj.leaf_start[y] = w.leaf_start[y];
+        lj.n_leaves[y] = p[y].n_leaves;
+        lj.leaf_sum[y] = leaf_sum[y];
+        cj.nodes[y] = (const PwFrontNode *)(w.blob + off_front[y]);
+        cj.n_nodes[y] = (int)p[y].front.size();
+        cj.leaf_sum[y] = leaf_sum[y];
+        cj.node_sum[y] = node_sum[y];
+        max_leaves = std::max(max_leaves, p[y].n_leaves);
+        max_front = std::max(max_front, (int)p[y].front.size());
+    }
+    lj.ap = ApTerm{tps, fps, T};
+    lj.roc = RocTerm{w.tps_k, w.fps_k, tps + (T - 1), fps + (T - 1)};
+    leaf_bounds_kernel<<<dim3((unsigned)((max_leaves + 1 + 255) / 256), 2), 256, 0, st>>>(tt);
+    MSS_CHECK_LAUNCH();
+    leaf_sum_kernel<<<dim3((unsigned)((max_leaves * 8 + 255) / 256), 2), 256, 0, st>>>(lj);
+    MSS_CHECK_LAUNCH();
+    subtree_combine_kernel<<<dim3((max_front + 127) / 128, 2), 128, 0, st>>>(cj);
+    MSS_CHECK_LAUNCH();
+
+    const size_t n_res = 8 + p[0].front.size() + p[1].front.size();
+    std::vector<double> h(n_res);
+    MSS_CHECK_CUDA(cudaMemcpyAsync(h.data(), w.results, n_res * 8, cudaMemcpyDeviceToHost, st));
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    size_t nx = 0;
+    const double ap_sum = pw_combine_top(h.data() + 8, nx, T, p[0].F);
+    nx = 0;
+    const double auroc = pw_combine_top(h.data() + 8 + p[0].front.size(), nx, T_roc, p[1].F);
+    const double ap = -ap_sum;
+    out_host[0] = auroc;                  // auc(): direction == 1 because fpr is non-decreasing
+    out_host[1] = ap > 0.0 ? ap : 0.0;    // max(0.0, -sum(...))
+    out_host[2] = h[0];
+    return MSS_OK;
+}
+
 }  // namespace mss
 
 using namespace mss;
 
-extern "C" size_t mss_counts_workspace_bytes(int64_t n) {
-    if (n < 0) n = 0;
-    return ct_tiles(n) * (sizeof(uint2) + sizeof(Pair64)) + 1024;
-}
+extern "C" size_t mss_counts_workspace_bytes(int64_t n) { return counts_ws_bytes(n); }
 
-extern "C" int mss_counts_from_sorted(const uint32_t *keys, const uint8_t *labs, int64_t n, int64_t pos_before,
-                                      int64_t idx_before, int64_t *tps, int64_t *fps, int64_t *T_host,
-                                      int64_t pn_host[2], void *workspace, size_t workspace_bytes, void *stream) {
-    MSS_REQUIRE(n >= 0 && T_host && pn_host, "mss_counts_from_sorted: bad arguments");
-    *T_host = 0; pn_host[0] = pn_host[1] = 0;
+extern "C" int mss_counts_from_sorted(const uint32_t *neg_keys, int64_t n_neg, const uint32_t *pos_keys, int64_t n_pos,
+                                      int64_t pos_before, int64_t neg_before, int64_t *tps, int64_t *fps, int64_t *T_host,
+                                      void *workspace, size_t workspace_bytes, void *stream) {
+    MSS_REQUIRE(n_neg >= 0 && n_pos >= 0 && T_host, "mss_counts_from_sorted: bad arguments");
+    *T_host = 0;
+    const int64_t n = n_neg + n_pos;
     if (n == 0) return MSS_OK;
-    MSS_REQUIRE(keys && labs && tps && fps && workspace, "mss_counts_from_sorted: null pointer");
-    const size_t tiles = ct_tiles(n);
-    MSS_REQUIRE(tiles < (1ull << 31), "mss_counts_from_sorted: n too large");
-    Carver c(workspace, workspace_bytes);
-    uint2 *sums = c.take<uint2>(tiles);
-    Pair64 *excl = c.take<Pair64>(tiles);
-    unsigned long long *totals = c.take<unsigned long long>(2);
-    if (!c.ok()) {
+    MSS_REQUIRE((n_neg == 0 || neg_keys) && (n_pos == 0 || pos_keys) && tps && fps && workspace, "mss_counts_from_sorted: null pointer");
+    CountsWs w;
+    if (!carve_counts(workspace, workspace_bytes, n, w)) {
         set_error("mss_counts_from_sorted: workspace too small (%zu < %zu)", workspace_bytes, mss_counts_workspace_bytes(n));
         return MSS_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    runs_kernel<false><<<(unsigned)tiles, CT_THREADS, 0, st>>>(keys, labs, n, sums, nullptr, 0, 0, nullptr, nullptr);
-    MSS_CHECK_LAUNCH();
-    tile_scan_kernel<<<1, 1024, 0, st>>>(sums, (long long)tiles, excl, totals);
-    MSS_CHECK_LAUNCH();
-    runs_kernel<true><<<(unsigned)tiles, CT_THREADS, 0, st>>>(keys, labs, n, nullptr, excl, pos_before, idx_before,
-                                                             (long long *)tps, (long long *)fps);
-    MSS_CHECK_LAUNCH();
-    unsigned long long h[2];
-    MSS_CHECK_CUDA(cudaMemcpyAsync(h, totals, sizeof(h), cudaMemcpyDeviceToHost, st));
+    int rc = plan_enqueue(w.plan, neg_keys, n_neg, pos_keys, n_pos, st);
+    if (rc) return rc;
+    rc = counts_enqueue(w.plan, n, pos_before, neg_before, tps, fps, w, st);
+    if (rc) return rc;
+    unsigned long long h = 0;
+    MSS_CHECK_CUDA(cudaMemcpyAsync(&h, w.totals, 8, cudaMemcpyDeviceToHost, st));
     MSS_CHECK_CUDA(cudaStreamSynchronize(st));
-    *T_host = (int64_t)h[0];
-    pn_host[0] = (int64_t)h[1];
-    pn_host[1] = n - (int64_t)h[1];
+    *T_host = (int64_t)h;
     return MSS_OK;
 }
 
-static size_t pw_device_bytes() {
-    return 2 * align_up(PW_MAX_SIZES * 8, 256) + align_up(PW_MAX_FRONT * sizeof(PwFrontNode), 256) +
-           align_up(PW_MAX_FRONT * 8, 256);
-}
+extern "C" size_t mss_tail_workspace_bytes(int64_t T) { return tail_ws_bytes(T); }
 
-extern "C" size_t mss_tail_workspace_bytes(int64_t T) {
-    if (T < 0) T = 0;
-    const size_t leaves = (size_t)T / 64 + 2;
-    return 2 * align_up((size_t)T * 8, 256)                      /* tps_k, fps_k */
-           + ct_tiles(T) * (sizeof(uint2) + sizeof(Pair64) + sizeof(Best)) + 1024   /* compaction tiles, FPR95 candidates */
-           + 2 * align_up(leaves * 8, 256)                       /* leaf sums (AP, ROC) */
-           + 2 * align_up((leaves + 1) * 8, 256)                 /* leaf starts (AP, ROC) */
-           + 2 * pw_device_bytes()                               /* tree tables + frontier (AP, ROC) */
-           + 1024 * sizeof(Best) + 8192;
-}
-
-static PwDevice pw_carve(Carver &c, size_t max_leaves) {
-    PwDevice d;
-    d.leaf_start = c.take<long long>(max_leaves + 1);
-    d.size = c.take<long long>(PW_MAX_SIZES);
-    d.leaves = c.take<long long>(PW_MAX_SIZES);
-    d.front = c.take<PwFrontNode>(PW_MAX_FRONT);
-    d.node_sum = c.take<double>(PW_MAX_FRONT);
-    return d;
-}
-
-// upload the plan, sum the leaves, combine below the frontier; frontier sums stay on the device
-template <typename Term>
-static int pw_launch(const PwPlan &p, const PwDevice &d, Term term, double *leaf_sum, cudaStream_t st) {
-    MSS_CHECK_CUDA(cudaMemcpyAsync(d.size, p.size.data(), p.size.size() * 8, cudaMemcpyHostToDevice, st));
-    MSS_CHECK_CUDA(cudaMemcpyAsync(d.leaves, p.leaves.data(), p.leaves.size() * 8, cudaMemcpyHostToDevice, st));
-    MSS_CHECK_CUDA(cudaMemcpyAsync(d.front, p.front.data(), p.front.size() * sizeof(PwFrontNode), cudaMemcpyHostToDevice, st));
-    PwTree tree{d.size, d.leaves, (int)p.size.size(), p.n, p.n_leaves};
-    leaf_bounds_kernel<<<(unsigned)((p.n_leaves + 1 + 255) / 256), 256, 0, st>>>(tree, d.leaf_start);
-    MSS_CHECK_LAUNCH();
-    leaf_sum_kernel<Term><<<(unsigned)((p.n_leaves * 8 + 255) / 256), 256, 0, st>>>(term, d.leaf_start, p.n_leaves, leaf_sum);
-    MSS_CHECK_LAUNCH();
-    const int nf = (int)p.front.size();
-    subtree_combine_kernel<<<(nf + 127) / 128, 128, 0, st>>>(d.front, nf, leaf_sum, d.node_sum);
-    MSS_CHECK_LAUNCH();
-    return MSS_OK;
-}
-
-extern "C" int mss_metrics_tail(const int64_t *tps_, const int64_t *fps_, int64_t T, double recall_level,
+extern "C" int mss_metrics_tail(const int64_t *tps, const int64_t *fps, int64_t T, double recall_level,
                                 void *workspace, size_t workspace_bytes, double out_host[3], int64_t *T_roc_host,
                                 void *stream) {
-    MSS_REQUIRE(tps_ && fps_ && T >= 1 && workspace && out_host, "mss_metrics_tail: bad arguments");
-    const long long *tps = (const long long *)tps_, *fps = (const long long *)fps_;
+    MSS_REQUIRE(tps && fps && T >= 1 && workspace && out_host, "mss_metrics_tail: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t tiles = ct_tiles(T);
-    const size_t max_leaves = (size_t)T / 64 + 2;
-    Carver c(workspace, workspace_bytes);
-    long long *tps_k = c.take<long long>((size_t)T);
-    long long *fps_k = c.take<long long>((size_t)T);
-    uint2 *sums = c.take<uint2>(tiles);
-    Pair64 *excl = c.take<Pair64>(tiles);
-    Best *tile_best = c.take<Best>(tiles);
-    double *sum_ap = c.take<double>(max_leaves);
-    double *sum_roc = c.take<double>(max_leaves);
-    PwDevice d_ap = pw_carve(c, max_leaves), d_roc = pw_carve(c, max_leaves);
-    Best *partial = c.take<Best>(1024);
-    unsigned long long *totals = c.take<unsigned long long>(2);
-    double *fpr_out = c.take<double>(1);
-    long long *fpr_k = c.take<long long>(1);
-    if (!c.ok()) {
+    TailWs w;
+    if (!carve_tail(workspace, workspace_bytes, T, w)) {
         set_error("mss_metrics_tail: workspace too small (%zu < %zu)", workspace_bytes, mss_tail_workspace_bytes(T));
         return MSS_ERR_WORKSPACE;
     }
-    // P, N = last entries (the kernels read them from the device; the host copy is for the empty-class check)
+    int rc = tail1_enqueue(tps, fps, nullptr, T, recall_level, w, st);
+    if (rc) return rc;
+    // T_roc shapes the ROC tree; P, N decide the empty-class outcome
+    unsigned long long h_troc = 0;
     long long PN[2];
+    MSS_CHECK_CUDA(cudaMemcpyAsync(&h_troc, w.totals, 8, cudaMemcpyDeviceToHost, st));
     MSS_CHECK_CUDA(cudaMemcpyAsync(&PN[0], tps + (T - 1), 8, cudaMemcpyDeviceToHost, st));
     MSS_CHECK_CUDA(cudaMemcpyAsync(&PN[1], fps + (T - 1), 8, cudaMemcpyDeviceToHost, st));
-
-    // ROC compaction (count, scan, scatter)
-    roc_compact_kernel<false><<<(unsigned)tiles, CT_THREADS, 0, st>>>(tps, fps, T, recall_level, sums, tile_best, nullptr,
-                                                                      nullptr, nullptr);
-    MSS_CHECK_LAUNCH();
-    tile_scan_kernel<<<1, 1024, 0, st>>>(sums, (long long)tiles, excl, totals);
-    MSS_CHECK_LAUNCH();
-    roc_compact_kernel<true><<<(unsigned)tiles, CT_THREADS, 0, st>>>(tps, fps, T, recall_level, nullptr, nullptr, excl,
-                                                                     tps_k, fps_k);
-    MSS_CHECK_LAUNCH();
-    // FPR95: tile candidates -> (<= 1024 candidates) -> result
-    {
-        const Best *cand = tile_best;
-        int ncand = (int)tiles;
-        if (tiles > 1024) {
-            fpr_reduce_kernel<<<1024, CT_THREADS, 0, st>>>(tile_best, (long long)tiles, partial);
-            MSS_CHECK_LAUNCH();
-            cand = partial;
-            ncand = 1024;
-        }
-        fpr_final_kernel<<<1, CT_THREADS, 0, st>>>(cand, ncand, fps, T, fpr_out, fpr_k);
-        MSS_CHECK_LAUNCH();
-    }
-    unsigned long long h_tot[2];
-    MSS_CHECK_CUDA(cudaMemcpyAsync(h_tot, totals, sizeof(h_tot), cudaMemcpyDeviceToHost, st));
-
-    // AP and FPR95 need nothing from the host: enqueue them behind the compaction
-    PwPlan p_ap, p_roc;
-    if (!pw_plan(T, p_ap) || (size_t)p_ap.n_leaves > max_leaves) {
-        set_error("mss_metrics_tail: internal pairwise-plan bound exceeded (T=%lld)", (long long)T);
-        return MSS_ERR_WORKSPACE;
-    }
-    int rc = pw_launch(p_ap, d_ap, ApTerm{tps, fps, T}, sum_ap, st);
-    if (rc) return rc;
-
-    MSS_CHECK_CUDA(cudaStreamSynchronize(st));      // T_roc decides the shape of the ROC tree
-    const long long T_roc = (long long)h_tot[0];
-    if (T_roc_host) *T_roc_host = T_roc;
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (T_roc_host) *T_roc_host = (int64_t)h_troc;
     if (PN[0] <= 0 || PN[1] <= 0) {
         set_error("mss_metrics_tail: P=%lld N=%lld (a class is empty)", PN[0], PN[1]);
         return MSS_EMPTY_CLASS;
     }
-    if (!pw_plan(T_roc, p_roc) || (size_t)p_roc.n_leaves > max_leaves) {
-        set_error("mss_metrics_tail: internal pairwise-plan bound exceeded (T_roc=%lld)", T_roc);
-        return MSS_ERR_WORKSPACE;
-    }
-    rc = pw_launch(p_roc, d_roc, RocTerm{tps_k, fps_k, tps + (T - 1), fps + (T - 1)}, sum_roc, st);
-    if (rc) return rc;
-
-    std::vector<double> h_ap(p_ap.front.size()), h_roc(p_roc.front.size());
-    double h_fpr = 0.0;
-    MSS_CHECK_CUDA(cudaMemcpyAsync(h_ap.data(), d_ap.node_sum, h_ap.size() * 8, cudaMemcpyDeviceToHost, st));
-    MSS_CHECK_CUDA(cudaMemcpyAsync(h_roc.data(), d_roc.node_sum, h_roc.size() * 8, cudaMemcpyDeviceToHost, st));
-    MSS_CHECK_CUDA(cudaMemcpyAsync(&h_fpr, fpr_out, 8, cudaMemcpyDeviceToHost, st));
-    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
-    size_t nx = 0;
-    const double auroc = pw_combine_top(h_roc.data(), nx, T_roc, p_roc.F);
-    nx = 0;
-    const double ap_sum = pw_combine_top(h_ap.data(), nx, T, p_ap.F);
-    const double ap = -ap_sum;
-    out_host[0] = auroc;                  // auc(): direction == 1 because fpr is non-decreasing
-    out_host[1] = ap > 0.0 ? ap : 0.0;    // max(0.0, -sum(...))
-    out_host[2] = h_fpr;
-    return MSS_OK;
+    return tail2_run(tps, fps, T, (int64_t)h_troc, w, st, out_host);
 }
 
 /* test hook (host only): bounds of leaf `leaf` of numpy's pairwise tree over n terms, computed by the same
@@ -744,44 +854,66 @@ extern "C" int mss_pairwise_sum_host(const double *terms_host, int64_t n, double
 }
 
 // ---- composites ------------------------------------------------------------------------------------
-static size_t one_shot_layout(int64_t n, size_t off[6]) {
-    // [keys n*4][labs n][state][sort ws][tps n*8][fps n*8][counts ws][tail ws]
+// one-shot layout: [keys n*4][state][sort ws][tps n*8][fps n*8][counts ws][tail ws]
+static size_t one_shot_layout(int64_t n, size_t off[7]) {
     size_t o = 0;
-    off[0] = o; o += align_up((size_t)n * 4, 256);
-    off[1] = o; o += align_up((size_t)n, 256);
-    off[2] = o; o += 256;
-    off[3] = o; o += align_up(mss_sort_pairs_workspace_bytes(n), 256);
-    off[4] = o; o += 2 * align_up((size_t)n * 8, 256);
-    off[5] = o; o += align_up(mss_counts_workspace_bytes(n), 256) + align_up(mss_tail_workspace_bytes(n), 256);
+    off[0] = o; o += align_up(((size_t)n + 4) * 4, 256);
+    off[1] = o; o += 256;
+    off[2] = o; o += align_up(sort_ws_bytes(n), 256);
+    off[3] = o; o += align_up((size_t)n * 8, 256);
+    off[4] = o; o += align_up((size_t)n * 8, 256);
+    off[5] = o; o += align_up(counts_ws_bytes(n), 256);
+    off[6] = o; o += align_up(tail_ws_bytes(n), 256);
     return o;
 }
 
 extern "C" size_t mss_ood_metrics_workspace_bytes(int64_t n) {
-    size_t off[6];
+    size_t off[7];
     return one_shot_layout(n < 0 ? 0 : n, off) + 256;
 }
 
-static int metrics_from_pairs(uint32_t *keys, uint8_t *labs, int64_t m, char *ws_sort, size_t sort_bytes,
-                              int64_t *tps, int64_t *fps, char *ws_rest, size_t rest_bytes, double out_host[3],
-                              int64_t counts_host[4], void *stream) {
-    int rc = mss_sort_pairs(keys, labs, m, ws_sort, sort_bytes, stream);
-    if (rc) return rc;
-    int64_t T = 0, pn[2];
-    const size_t cbytes = align_up(mss_counts_workspace_bytes(m), 256);
-    rc = mss_counts_from_sorted(keys, labs, m, 0, 0, tps, fps, &T, pn, ws_rest, cbytes, stream);
-    if (rc) return rc;
-    int64_t T_roc = 0;
-    rc = mss_metrics_tail(tps, fps, T, 0.95, ws_rest + cbytes, rest_bytes - cbytes, out_host, &T_roc, stream);
-    if (rc) return rc;
-    if (counts_host) { counts_host[0] = pn[0]; counts_host[1] = pn[1]; counts_host[2] = T; counts_host[3] = T_roc; }
+static int check_state(const EvalState &h) {
+    // the reference checks emptiness first (metric.py:176), sklearn validates finiteness before anything else it does
+    if (h.n_pos == 0 || h.n_neg == 0) return MSS_EMPTY_CLASS;
+    if (h.nan_flag) { set_error("Input contains NaN."); return MSS_ERR_NAN; }
+    if (h.inf_flag) { set_error("Input contains infinity or a value too large for dtype('float32')."); return MSS_ERR_INF; }
     return MSS_OK;
 }
 
-static int check_state(const int64_t st[4]) {
-    if (st[2]) { set_error("Input contains NaN."); return MSS_ERR_NAN; }
-    if (st[3]) { set_error("Input contains infinity or a value too large for dtype('float32')."); return MSS_ERR_INF; }
-    if (st[1] == 0 || st[1] == st[0]) return MSS_EMPTY_CLASS;
-    return MSS_OK;
+// Everything up to the point where the host must know T / T_roc is enqueued without a round trip: the stream sizes
+// are read by the kernels from the evaluator state, grids are sized for n_upper.  ONE synchronisation fetches the
+// state and the two totals, a second one the leaf sums.
+static int metrics_speculative(const mss_eval_buffers *ev, int64_t n_upper, char *ws_sort, size_t sort_b, int64_t *tps,
+                               int64_t *fps, char *ws_counts, size_t counts_b, char *ws_tail, size_t tail_b,
+                               double out_host[3], int64_t counts_host[4], cudaStream_t st) {
+    const SortPlan *plan = nullptr;
+    int rc = sort_enqueue(ev, nullptr, 0, nullptr, 0, n_upper, ws_sort, sort_b, st, &plan);
+    if (rc) return rc;
+    CountsWs cw;
+    TailWs tw;
+    if (!carve_counts(ws_counts, counts_b, n_upper, cw) || !carve_tail(ws_tail, tail_b, n_upper, tw)) {
+        set_error("mss_ood_metrics: workspace too small");
+        return MSS_ERR_WORKSPACE;
+    }
+    rc = counts_enqueue(plan, n_upper, 0, 0, tps, fps, cw, st);
+    if (rc) return rc;
+    rc = tail1_enqueue(tps, fps, cw.totals, 0, 0.95, tw, st);
+    if (rc) return rc;
+    EvalState h;
+    unsigned long long h_T = 0, h_Troc = 0;
+    MSS_CHECK_CUDA(cudaMemcpyAsync(&h, ev->state, sizeof(h), cudaMemcpyDeviceToHost, st));
+    MSS_CHECK_CUDA(cudaMemcpyAsync(&h_T, cw.totals, 8, cudaMemcpyDeviceToHost, st));
+    MSS_CHECK_CUDA(cudaMemcpyAsync(&h_Troc, tw.totals, 8, cudaMemcpyDeviceToHost, st));
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (h.overflow || (int64_t)(h.n_neg + h.n_pos) > ev->capacity) {
+        set_error("evaluator capacity %lld exceeded (%llu valid pixels appended)", (long long)ev->capacity,
+                  (unsigned long long)(h.n_neg + h.n_pos + h.overflow));
+        return MSS_ERR_WORKSPACE;
+    }
+    rc = check_state(h);
+    if (rc) return rc;
+    if (counts_host) { counts_host[0] = (int64_t)h.n_pos; counts_host[1] = (int64_t)h.n_neg; counts_host[2] = (int64_t)h_T; counts_host[3] = (int64_t)h_Troc; }
+    return tail2_run(tps, fps, (int64_t)h_T, (int64_t)h_Troc, tw, st, out_host);
 }
 
 extern "C" int mss_ood_metrics(const float *scores, const void *labels, int label_dtype, int64_t n, int64_t id_in,
@@ -790,50 +922,56 @@ extern "C" int mss_ood_metrics(const float *scores, const void *labels, int labe
     MSS_REQUIRE(n >= 0 && out_host, "mss_ood_metrics: bad arguments");
     if (n == 0) return MSS_EMPTY_CLASS;
     MSS_REQUIRE(scores && labels && workspace, "mss_ood_metrics: null pointer");
-    size_t off[6];
+    size_t off[7];
     const size_t need = one_shot_layout(n, off);
     char *ws = (char *)align_up((size_t)(uintptr_t)workspace, 256);
     if ((size_t)(ws - (char *)workspace) + need > workspace_bytes) {
         set_error("mss_ood_metrics: workspace too small (%zu < %zu)", workspace_bytes, mss_ood_metrics_workspace_bytes(n));
         return MSS_ERR_WORKSPACE;
     }
-    mss_eval_buffers ev{(uint32_t *)(ws + off[0]), (uint8_t *)(ws + off[1]), ws + off[2], n};
+    mss_eval_buffers ev{(uint32_t *)(ws + off[0]), ws + off[1], n};
     int rc = mss_eval_reset(&ev, stream);
     if (rc) return rc;
     rc = mss_eval_append(scores, labels, label_dtype, n, id_in, id_out, &ev, stream);
     if (rc) return rc;
-    int64_t st[4];
-    rc = mss_eval_state_host(&ev, st, stream);
-    if (rc) return rc;
-    // sklearn validates before anything else, the reference checks emptiness first (metric.py:176)
-    if (st[1] == 0 || st[1] == st[0]) return MSS_EMPTY_CLASS;
-    rc = check_state(st);
-    if (rc) return rc;
-    return metrics_from_pairs(ev.keys, ev.labs, st[0], ws + off[3], off[4] - off[3], (int64_t *)(ws + off[4]),
-                              (int64_t *)(ws + off[4] + align_up((size_t)n * 8, 256)), ws + off[5], need - off[5],
-                              out_host, counts_host, stream);
+    return metrics_speculative(&ev, n, ws + off[2], off[3] - off[2], (int64_t *)(ws + off[3]), (int64_t *)(ws + off[4]),
+                               ws + off[5], off[6] - off[5], ws + off[6], need - off[6], out_host, counts_host,
+                               (cudaStream_t)stream);
+}
+
+// From an evaluator: the host reads the state first (it also sizes the workspace), so every stage gets exact sizes.
+//   workspace >= mss_ood_metrics_from_eval_workspace_bytes(count)   with count = mss_eval_state_host()[0]
+extern "C" size_t mss_ood_metrics_from_eval_workspace_bytes(int64_t count) {
+    if (count < 0) count = 0;
+    return 256 + align_up(sort_ws_bytes(count), 256) + 2 * align_up((size_t)count * 8, 256) + align_up(counts_ws_bytes(count), 256) +
+           align_up(tail_ws_bytes(count), 256);
 }
 
 extern "C" int mss_ood_metrics_from_eval(const mss_eval_buffers *ev, void *workspace, size_t workspace_bytes,
                                          double out_host[3], int64_t counts_host[4], void *stream) {
-    MSS_REQUIRE(ev && ev->keys && ev->labs && ev->state && workspace && out_host, "mss_ood_metrics_from_eval: null pointer");
-    int64_t st[4];
-    int rc = mss_eval_state_host(ev, st, stream);
+    MSS_REQUIRE(ev && ev->keys && ev->state && workspace && out_host, "mss_ood_metrics_from_eval: null pointer");
+    int64_t s4[4];
+    int rc = mss_eval_state_host(ev, s4, stream);
     if (rc) return rc;
-    if (st[1] == 0 || st[1] == st[0]) return MSS_EMPTY_CLASS;
-    rc = check_state(st);
-    if (rc) return rc;
-    const int64_t m = st[0];
+    const int64_t m = s4[0];
+    if (s4[1] == 0 || s4[1] == m) return MSS_EMPTY_CLASS;
+    if (s4[2]) { set_error("Input contains NaN."); return MSS_ERR_NAN; }
+    if (s4[3]) { set_error("Input contains infinity or a value too large for dtype('float32')."); return MSS_ERR_INF; }
     char *ws = (char *)align_up((size_t)(uintptr_t)workspace, 256);
     const size_t lead = (size_t)(ws - (char *)workspace);
-    const size_t sort_b = align_up(mss_sort_pairs_workspace_bytes(m), 256);
-    const size_t cnt_b = 2 * align_up((size_t)m * 8, 256);
-    const size_t rest_b = align_up(mss_counts_workspace_bytes(m), 256) + align_up(mss_tail_workspace_bytes(m), 256);
-    if (lead + sort_b + cnt_b + rest_b > workspace_bytes) {
-        set_error("mss_ood_metrics_from_eval: workspace too small (%zu < %zu)", workspace_bytes, lead + sort_b + cnt_b + rest_b);
+    const size_t sort_b = align_up(sort_ws_bytes(m), 256), cnt_b = align_up((size_t)m * 8, 256);
+    const size_t cw_b = align_up(counts_ws_bytes(m), 256), tw_b = align_up(tail_ws_bytes(m), 256);
+    if (lead + sort_b + 2 * cnt_b + cw_b + tw_b > workspace_bytes) {
+        set_error("mss_ood_metrics_from_eval: workspace too small (%zu < %zu)", workspace_bytes, lead + sort_b + 2 * cnt_b + cw_b + tw_b);
         return MSS_ERR_WORKSPACE;
     }
-    return metrics_from_pairs(ev->keys, ev->labs, m, ws, sort_b, (int64_t *)(ws + sort_b),
-                              (int64_t *)(ws + sort_b + align_up((size_t)m * 8, 256)), ws + sort_b + cnt_b, rest_b,
-                              out_host, counts_host, stream);
+    return metrics_speculative(ev, m, ws, sort_b, (int64_t *)(ws + sort_b), (int64_t *)(ws + sort_b + cnt_b), ws + sort_b + 2 * cnt_b,
+                               cw_b, ws + sort_b + 2 * cnt_b + cw_b, tw_b, out_host, counts_host, (cudaStream_t)stream);
+}
+
+/* stage-level: sort both streams of an evaluator in place (the multi-GPU evaluator sorts, counts and runs the tail as
+ * separate steps around its collectives).  n_upper >= the number of stored keys. */
+extern "C" int mss_eval_sort(const mss_eval_buffers *ev, int64_t n_upper, void *workspace, size_t workspace_bytes, void *stream) {
+    MSS_REQUIRE(ev && ev->keys && ev->state && workspace && n_upper >= 0, "mss_eval_sort: bad arguments");
+    return sort_enqueue(ev, nullptr, 0, nullptr, 0, n_upper, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
 }

@@ -1,20 +1,26 @@
-// Stable LSD radix sort of (uint32 key, uint8 label) pairs -- the GPU replacement for the three
-// full argsorts the reference performs per evaluation (sklearn _ranking.py:909 inside roc_auc_score and
-// again inside average_precision_score, plus np.argsort(kind="mergesort") at lib/utils/metric.py:103).
+// Stable LSD radix sort of uint32 keys -- the GPU replacement for the three full argsorts the reference
+// performs per evaluation (sklearn _ranking.py:909 inside roc_auc_score and again inside
+// average_precision_score, plus np.argsort(kind="mergesort") at lib/utils/metric.py:103).
 //
-// "Onesweep": one upfront histogram of all four 8-bit digits, then four scatter passes, each reading
-// and writing every pair exactly once; the cross-tile digit offsets come from a decoupled look-back
-// over per-tile status words instead of a separate scan pass.
-//   HBM traffic per pair: 4 (histogram read) + 4 x (4+1 read + 4+1 write) = 44 B.
-// Tile = 256 threads x 16 keys.  Ranking inside a tile is stable and atomics-free: keys are
-// warp-striped, each warp ranks its 512 keys item by item with match.any, warps are combined by a
-// per-digit prefix over the 8 warps.
+// Round 2: KEY-ONLY and SEGMENTED.  The evaluator keeps in-distribution and OOD keys in two streams (eval_append.cuh),
+// so the label is never carried through the sort: 4 + 4 x (4 + 4) = 36 B of HBM traffic per key instead of the 44 B per
+// (key, u8 label) pair of round 1, no 1-byte scatter (ncu, round 1: 2.2x store-sector inflation), and no label staging
+// in shared memory.  Both streams are sorted by ONE sequence of launches: tiles are numbered over both segments and a
+// tile's look-back stops at the first tile of its own segment.
 //
-// The same scatter kernel, with the digit replaced by "which key range does this key fall in"
-// (SplitterDigit), is the local half of the multi-GPU key-range exchange (mss_partition_pairs).
+// "Onesweep": one upfront histogram of all four 8-bit digits, then four scatter passes, each reading and writing every
+// key exactly once; the cross-tile digit offsets come from a decoupled look-back over per-tile status words instead of
+// a separate scan pass.  A pass whose digit is the same for every key of a segment (fp16-born or quantised scores
+// leave the low byte constant) is skipped for that segment; the decision is taken on the device from the histogram.
+// Tile = 256 threads x 16 keys.  Ranking inside a tile is stable and atomics-free: keys are warp-striped, each warp
+// ranks its 512 keys item by item with ballots, warps are combined by a per-digit prefix over the 8 warps.
+//
+// The same tile routine, with the digit replaced by "which key range does this key fall in" (SplitterDigit), is the
+// local half of the multi-GPU key-range exchange: bucket d is stored straight into rank d's receive buffer
+// (mss_partition_scatter_keys).
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "sort_plan.cuh"
 
 namespace mss {
 
@@ -26,23 +32,32 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int LB_WINDOW = 8;                        // look-back statuses fetched per round trip (16: 39.7 vs 40.8 Gpairs/s)
 
 struct ShiftDigit {
+    static constexpr bool kCheap = true;
     int shift;
     __device__ __forceinline__ unsigned operator()(uint32_t k) const { return (k >> shift) & 255u; }
 };
 
-// dest(key) = #{ j : key >= splitter[j] }  (splitters ascending, parts-1 of them, parts <= 256)
+// dest(key) = #{ j : key >= splitter[j] }  (splitters ascending, nspl = parts - 1 <= 255 of them).
+// `spl` points at a SHARED-memory copy inside the kernels; branchless lower bound over 2^steps - 1 slots, the slots past
+// nspl acting as +infinity.
 struct SplitterDigit {
+    static constexpr bool kCheap = false;
     const uint32_t *spl;
-    int nspl;
+    int nspl, steps;
     __device__ __forceinline__ unsigned operator()(uint32_t k) const {
-        int lo = 0, hi = nspl;  // first j with spl[j] > k
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (__ldg(spl + mid) <= k) lo = mid + 1; else hi = mid;
+        unsigned lo = 0;
+        for (int s = 1 << (steps - 1); s > 0; s >>= 1) {
+            const unsigned idx = lo + s - 1;
+            lo += ((int)idx < nspl && k >= spl[idx]) ? s : 0;
         }
-        return (unsigned)lo;
+        return lo;
     }
 };
+static int splitter_steps(int parts) {
+    int steps = 1;
+    while ((1 << steps) - 1 < parts - 1) steps++;
+    return steps;
+}
 
 // Lanes holding the same BITS-bit value as this lane, from BITS ballots.  (match.any does the same in one
 // instruction but costs ~200 cycles per warp on sm_100 when the 32 values are distinct -- measured with
@@ -60,6 +75,30 @@ __device__ __forceinline__ unsigned match_bits(unsigned d, bool valid) {
     return peers;
 }
 
+// ---- the plan -------------------------------------------------------------------------------------------
+__global__ void sort_plan_kernel(SortPlan *plan, uint32_t *xa, uint32_t *ya, long long na, uint32_t *xb, uint32_t *yb,
+                                 long long nb, const EvalState *state, uint32_t *keys, uint32_t *alt, long long capacity) {
+    if (state) {
+        // evaluator streams: negatives at keys[0, n_neg), positives at keys[capacity - n_pos, capacity)
+        na = (long long)min(state->n_neg, (unsigned long long)capacity);
+        nb = (long long)min(state->n_pos, (unsigned long long)(capacity - na));
+        xa = keys;
+        xb = keys + (capacity - nb);
+        ya = alt;
+        yb = alt + ((na + 3) & ~3ll);
+    }
+    SortPlan p;
+    p.seg[0] = SortSeg{xa, ya, na, 0u, (unsigned)((na + SORT_TILE - 1) / SORT_TILE)};
+    p.seg[1] = SortSeg{xb, yb, nb, p.seg[0].tiles, (unsigned)((nb + SORT_TILE - 1) / SORT_TILE)};
+    p.total_tiles = p.seg[0].tiles + p.seg[1].tiles;
+    for (int s = 0; s < 2; s++) {
+        for (int q = 0; q < 4; q++) p.sel[s][q] = (unsigned char)(q & 1);
+        p.copy_back[s] = 0;
+    }
+    p.pad = 0;
+    *plan = p;
+}
+
 // ---- upfront histogram of the four digits ------------------------------------------------------------
 // Shared-memory atomics cost ~1-2 cycles per LANE on sm_100 and the digits of real score distributions are
 // extremely skewed (sign/exponent bits; zeroed mantissa bits of fp16-born scores), so contention-sensitive
@@ -75,6 +114,7 @@ __device__ __forceinline__ unsigned match_bits(unsigned d, bool valid) {
 //   * a lane adds at most 16 to one counter per chunk, so counters are folded into 32-bit per-CTA totals every
 //     HIST_EPOCH (<= 4095) chunks -- warp-local, no CTA barrier.
 // Two keys are in flight per lane; when they hit the same counter both store the merged total.
+// blockIdx.y = segment of the plan; a segment uses as many of the gridDim.x CTAs as it has work for.
 constexpr int HIST_WARPS = 12;
 constexpr int HIST_THREADS = HIST_WARPS * 32;                  // 384
 constexpr int HIST_GROUPS = HIST_WARPS / 4;                    // 3
@@ -96,9 +136,16 @@ __device__ __forceinline__ void sts_u16(uint32_t a, unsigned v) {
 }
 
 __global__ void __launch_bounds__(HIST_THREADS, 1)
-radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned long long *__restrict__ hist,
-                       int epoch_chunks) {
+radix_histogram_kernel(const SortPlan *__restrict__ plan, unsigned long long *__restrict__ hist_all, int epoch_chunks) {
     extern __shared__ __align__(128) unsigned char s_raw[];
+    const SortSeg seg = plan->seg[blockIdx.y];
+    const uint32_t *__restrict__ keys = seg.x;
+    const long long n = seg.n;
+    unsigned long long *__restrict__ hist = hist_all + blockIdx.y * 4 * RADIX;
+    // CTAs this segment employs: >= 4 chunks per CTA
+    const unsigned grid = (unsigned)max(1ll, min((long long)gridDim.x, (n + 4 * HIST_CHUNK_KEYS - 1) / (4 * HIST_CHUNK_KEYS)));
+    if (n == 0 || blockIdx.x >= grid) return;
+
     unsigned char *s_cnt = s_raw;                                                  // [12][256][32] u16
     uint4 *s_ring = reinterpret_cast<uint4 *>(s_raw + HIST_WARPS * HIST_WARP_BYTES);   // [4][384] uint4
     unsigned *s_tot = reinterpret_cast<unsigned *>(s_ring + HIST_STAGES * (HIST_CHUNK_KEYS / 4));   // [4][256]
@@ -121,9 +168,9 @@ radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned 
     const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + head);
     const long long chunks = (groups4 + HIST_CHUNK_KEYS / 4 - 1) / (HIST_CHUNK_KEYS / 4);
     // CTA c owns chunks c, c + grid, ...
-    const long long my_chunks = (chunks > (long long)blockIdx.x) ? (chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long my_chunks = (chunks > (long long)blockIdx.x) ? (chunks - blockIdx.x + grid - 1) / grid : 0;
     auto issue = [&](long long j) {                                                // elected lane only
-        const long long c = (long long)blockIdx.x + j * gridDim.x;
+        const long long c = (long long)blockIdx.x + j * grid;
         const long long g0 = c * (HIST_CHUNK_KEYS / 4);
         const unsigned bytes = (unsigned)(min((long long)(HIST_CHUNK_KEYS / 4), groups4 - g0) * 16);
         const int s = (int)(j % HIST_STAGES);
@@ -160,7 +207,7 @@ radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned 
         const int s = (int)(j % HIST_STAGES);
         const unsigned parity = (unsigned)((j / HIST_STAGES) & 1);
         mbar_wait(&s_full[s], parity);
-        const long long c = (long long)blockIdx.x + j * gridDim.x;
+        const long long c = (long long)blockIdx.x + j * grid;
         const int valid4 = (int)min((long long)(HIST_CHUNK_KEYS / 4), groups4 - c * (HIST_CHUNK_KEYS / 4));
         const uint4 *src = s_ring + s * (HIST_CHUNK_KEYS / 4) + group * 128 + lane;
 #pragma unroll
@@ -201,38 +248,45 @@ radix_histogram_kernel(const uint32_t *__restrict__ keys, long long n, unsigned 
         }
 }
 
-// hist[4][256] -> exclusive prefix per pass (in place), one warp-scan per pass
+// hist[seg][pass][256] -> exclusive prefix (in place), one warp-scan per (segment, pass); a digit whose histogram
+// has a single non-empty bin leaves every key where it is: the pass is skipped for that segment (allow_skip).
 __global__ void __launch_bounds__(RADIX)
-radix_scan_bins_kernel(unsigned long long *__restrict__ hist, int passes) {
+radix_scan_bins_kernel(unsigned long long *__restrict__ hist, SortPlan *plan, int allow_skip) {
     __shared__ unsigned long long s_warp[RADIX / 32];
-    for (int p = 0; p < passes; p++) {
-        unsigned long long v = hist[p * RADIX + threadIdx.x], inc = v;
+    __shared__ unsigned char s_skip[2][4];
+    for (int s = 0; s < 2; s++) {
+        const unsigned long long n = (unsigned long long)plan->seg[s].n;
+        for (int p = 0; p < 4; p++) {
+            unsigned long long *h = hist + (s * 4 + p) * RADIX;
+            unsigned long long v = h[threadIdx.x], inc = v;
+            const int single = __syncthreads_or(allow_skip && n > 0 && v == n);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
-            if ((threadIdx.x & 31) >= d) inc += t;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((threadIdx.x & 31) >= d) inc += t;
+            }
+            if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
+            __syncthreads();
+            unsigned long long base = 0;
+            for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += s_warp[w];
+            h[threadIdx.x] = base + inc - v;
+            if (threadIdx.x == 0) s_skip[s][p] = (unsigned char)(single || n == 0);
+            __syncthreads();
         }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
-        __syncthreads();
-        unsigned long long base = 0;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += s_warp[w];
-        hist[p * RADIX + threadIdx.x] = base + inc - v;
-        __syncthreads();
+    }
+    if (threadIdx.x < 2) {
+        const int s = threadIdx.x;
+        int cur = 0;                                         // 0: data in x, 1: data in y
+        for (int p = 0; p < 4; p++) {
+            if (s_skip[s][p]) plan->sel[s][p] = 2;
+            else { plan->sel[s][p] = (unsigned char)cur; cur ^= 1; }
+        }
+        plan->copy_back[s] = (unsigned char)cur;
     }
 }
 
 // ---- one scatter pass -----------------------------------------------------------------------------
-// tile_status[tile][digit]: bits 63..62 = 0 empty / 1 tile count / 2 inclusive prefix, low 62 bits = value.
-constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, VAL_MASK = (1ull << 62) - 1;
-
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
+// tile_status[tile][digit]: look-back status words (common.cuh)
 
 // 8-bit match for a tile without padding lanes: 4 instructions per bit (predicate, ballot, select, and)
 // Written in PTX so that one bit costs exactly predicate (and + setp -> one LOP3 with a predicate result), VOTE, SEL,
@@ -257,64 +311,69 @@ __device__ __forceinline__ unsigned match8_full(unsigned d) {
     return peers;
 }
 
+// DIG: the digit function is expensive (SplitterDigit): digits are computed once, kept packed in registers and
+// staged next to the keys for the write-out; the splitters sit in shared memory.
+template <bool DIG>
 struct SweepSmem {
     __align__(16) uint32_t keys[SORT_TILE];
-    __align__(16) uint8_t vals[SORT_TILE];
     unsigned warp_hist[SORT_WARPS][RADIX];   // per-warp digit counts -> exclusive scatter bases
-    unsigned long long global[RADIX];        // global output index of tile-sorted position 0 of each digit
+    unsigned long long global[RADIX];        // byte address of tile-sorted position 0 of each digit in the output
+    unsigned long long dst[RADIX];           // byte address where the first key with digit d of the whole segment goes
+    unsigned long long *status;              // status words of this segment's tile 0
     unsigned scan[SORT_WARPS];
-    unsigned tile;
-};
-// MULTI-destination scatter (multi-GPU exchange): bucket d goes to its own pair of buffers, which may live in
-// a PEER GPU's memory (NVLink stores); dst[d] / dst[RADIX + d] = base addresses of bucket d's key / label buffer
-struct MultiDst {
-    const unsigned long long *table;         // device array [2 * RADIX], or null: single destination (keys_out, vals_out)
+    // tile context (thread 0 -> everyone)
+    const uint32_t *in;
+    unsigned long long out;                  // byte address of the output array (sort passes)
+    long long n;
+    unsigned tile, seg;
+    int skip;
+    uint8_t dig[DIG ? SORT_TILE : 16];
+    uint32_t spl[DIG ? RADIX : 4];
 };
 
-// FULL: the tile holds exactly SORT_TILE pairs (every tile but possibly the last): no bounds predicates.
-template <typename DigitFn, bool FULL, bool MULTI>
-__device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__restrict__ keys_in,
-                                           uint32_t *__restrict__ keys_out, const uint8_t *__restrict__ vals_in,
-                                           uint8_t *__restrict__ vals_out, long long n,
-                                           const unsigned long long *__restrict__ bin_base,
-                                           unsigned long long *tile_status, DigitFn digit_of, unsigned tile,
-                                           MultiDst multi) {
+// One tile: rank, scatter into tile-sorted order in shared memory, look back, write out.
+//   sm.dst[d]  byte address where the FIRST key with digit d of the whole segment goes (written by thread d before)
+//   sm.status  status words of this segment's tile 0, `sstride` words per tile; nd live digits (threads d >= nd idle)
+// (both parked in shared memory: as arguments they stayed live in registers across the whole tile and the 64-register
+// kernel spilled)
+// FULL: the tile holds exactly SORT_TILE keys (every tile but possibly the last): no bounds predicates.
+template <typename DigitFn, bool FULL, bool DIG>
+__device__ __forceinline__ void sweep_tile(SweepSmem<DIG> &sm, int sstride, int nd, DigitFn digit_of) {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long tile_base = (long long)tile * SORT_TILE;
-    const int tile_n = FULL ? SORT_TILE : (int)(n - tile_base);
+    // (tile context is re-read from shared memory where it is needed instead of being carried in registers)
+    const int tile_n = FULL ? SORT_TILE : (int)(sm.n - (long long)sm.tile * SORT_TILE);
 
-    // labels of the tile: one coalesced 16-byte load per thread, staged in smem
-    {
-        const long long b = tile_base + (long long)tid * 16;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if ((FULL || b + 16 <= n) && ((((uintptr_t)vals_in) & 15) == 0)) {
-            v = *reinterpret_cast<const uint4 *>(vals_in + b);
-        } else {
-            uint8_t *pv = reinterpret_cast<uint8_t *>(&v);
-            for (int j = 0; j < 16; j++) pv[j] = (b + j < n) ? vals_in[b + j] : 0;
-        }
-        *reinterpret_cast<uint4 *>(sm.vals + tid * 16) = v;
-    }
     // keys, warp-striped: item i of lane l in warp w sits at w*512 + i*32 + l
     uint32_t key[SORT_IPT];
     const int wbase = warp * (32 * SORT_IPT) + lane;
-    const uint32_t *kp = keys_in + tile_base + wbase;
+    const uint32_t *kp = sm.in + (long long)sm.tile * SORT_TILE + wbase;
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) key[i] = (FULL || wbase + i * 32 < tile_n) ? __ldg(kp + i * 32) : 0u;
-    __syncthreads();   // vals staged, warp_hist zeroed (by the caller)
+
+    unsigned dpk[DIG ? SORT_IPT / 4 : 1];
+    if (DIG) {
+#pragma unroll
+        for (int i = 0; i < SORT_IPT; i++) {
+            const unsigned d = digit_of(key[i]);
+            dpk[i >> 2] = (i & 3) ? (dpk[i >> 2] | (d << (8 * (i & 3)))) : d;
+        }
+    }
+    auto dig = [&](int i) -> unsigned {
+        if (DIG) return (dpk[i >> 2] >> (8 * (i & 3))) & 255u;
+        return digit_of(key[i]);
+    };
 
     // phase 1 (independent, pipelined): lanes of my warp holding the same digit as my item i
     unsigned peers[SORT_IPT];
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
-        if (FULL) peers[i] = match8_full(digit_of(key[i]));
+        if (FULL) peers[i] = match8_full(dig(i));
         else {
             const bool valid = wbase + i * 32 < tile_n;
-            peers[i] = match_bits<8>(valid ? digit_of(key[i]) : 0u, valid);
+            peers[i] = match_bits<8>(valid ? dig(i) : 0u, valid);
         }
     }
     // phase 2 (serial per warp; item order == memory order, hence stable): running per-digit counters.
-    // rank[i] bit 15 carries the label so it needs no register of its own.
     // two 16-bit ranks per register (8 registers, not 16: the kernel has to fit 64 registers for 4 CTAs per SM)
     unsigned rank2[SORT_IPT / 2];
     const unsigned lt = lanemask_lt();
@@ -325,25 +384,24 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
         const unsigned below = __popc(peers[i] & lt);
         unsigned old = 0;
         if (below == 0 && valid) {
-            const unsigned d = digit_of(key[i]);
+            const unsigned d = dig(i);
             old = wh[d];
             wh[d] = old + __popc(peers[i]);
         }
         old = __shfl_sync(0xffffffffu, old, __ffs(peers[i]) - 1);
-        const unsigned r16 = (old + below) | ((unsigned)sm.vals[wbase + i * 32] << 15);
+        const unsigned r16 = old + below;
         rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r16 << 16)) : r16;
         __syncwarp();
     }
     __syncthreads();
 
-    // thread d: prefix over the 8 warps for digit d, tile count, publish, look back
+    // thread d: prefix over the 8 warps for digit d, tile count, publish
     {
-        const unsigned d = tid;
+        const unsigned d = tid, tile = sm.tile;
         unsigned cnt[SORT_WARPS], tot = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; w++) { cnt[w] = sm.warp_hist[w][d]; tot += cnt[w]; }
-        unsigned long long *my = tile_status + (size_t)tile * RADIX + d;
-        st_status(my, (tile == 0 ? FLAG_INC : FLAG_AGG) | tot);
+        if ((int)d < nd) st_status(sm.status + (size_t)tile * sstride + d, (tile == 0 ? FLAG_INC : FLAG_AGG) | tot);
 
         // exclusive scan of tot over the 256 digits -> first tile-sorted position of digit d
         unsigned inc = tot;
@@ -365,40 +423,39 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
     }
     __syncthreads();
 
-    // scatter into tile-sorted order in smem (labels were all read in phase 2, so vals can be overwritten).
-    // This needs only tile-local offsets, so it runs BEFORE the look-back: the predecessors get this much more
-    // time to publish their inclusive prefixes and the look-back below finds one after a window or two
-    // (ncu, round 1: look-back straight after the count walked ~26 tiles back and was 25 % of all instructions).
+    // scatter into tile-sorted order in smem.  This needs only tile-local offsets, so it runs BEFORE the look-back: the
+    // predecessors get this much more time to publish their inclusive prefixes and the look-back below finds one after a
+    // window or two (ncu, round 1: look-back straight after the count walked ~26 tiles back and was 25 % of all
+    // instructions).
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
         if (FULL || wbase + i * 32 < tile_n) {
             const unsigned r16 = (i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
-            const unsigned pos = wh[digit_of(key[i])] + (r16 & 0x7fffu);
+            const unsigned d = dig(i);
+            const unsigned pos = wh[d] + r16;
             sm.keys[pos] = key[i];
-            sm.vals[pos] = (uint8_t)(r16 >> 15);
+            if (DIG) sm.dig[pos] = (uint8_t)d;
         }
     }
 
     // Decoupled look-back, thread d for digit d, LB_WINDOW predecessors per round trip (the loads of one window
     // are independent, so they overlap); branch-light: one "all published?" test per window, predicated adds.
-    {
-        const unsigned d = tid;
+    if ((int)tid < nd) {
+        const unsigned d = tid, tile = sm.tile;
         const unsigned tot = (unsigned)sm.global[d], start = (unsigned)(sm.global[d] >> 32);
-        unsigned long long *my = tile_status + (size_t)tile * RADIX + d;
+        unsigned long long *my = sm.status + (size_t)tile * sstride + d;
         unsigned long long prefix = 0;
         if (tile > 0) {
-            // (First form: 64-bit tile index, a bounds predicate per load, flag tests on the 64-bit words -- 145 SASS
-            // instructions per window of 8, 3.5 windows per tile = 31 of the pass's 111 instructions per key.)
             int t = (int)tile - 1;                                  // tiles < 2^31 (host-checked)
-            const unsigned long long *p = tile_status + (size_t)t * RADIX + d;
+            const unsigned long long *p = my - sstride;
             for (;;) {
                 unsigned long long st[LB_WINDOW];
                 if (t >= LB_WINDOW - 1) {                           // CTA-uniform: all predecessors of the window exist
 #pragma unroll
-                    for (int j = 0; j < LB_WINDOW; j++) st[j] = ld_status(p - (size_t)j * RADIX);
+                    for (int j = 0; j < LB_WINDOW; j++) st[j] = ld_status(p - (size_t)j * sstride);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < LB_WINDOW; j++) st[j] = (j <= t) ? ld_status(p - (size_t)j * RADIX) : FLAG_INC;   // before tile 0: prefix 0
+                    for (int j = 0; j < LB_WINDOW; j++) st[j] = (j <= t) ? ld_status(p - (size_t)j * sstride) : FLAG_INC;   // before tile 0: prefix 0
                 }
                 // flags live in the top two bits: 32-bit tests on the high words
                 unsigned lowest = 0xffffffffu;
@@ -413,11 +470,12 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
                 }
                 if (done) break;
                 t -= LB_WINDOW;
-                p -= (size_t)LB_WINDOW * RADIX;
+                p -= (size_t)LB_WINDOW * sstride;
             }
             st_status(my, FLAG_INC | (prefix + tot));
         }
-        sm.global[d] = bin_base[d] + prefix - start;       // (only thread d ever touches sm.global[d] up to here)
+        // byte address of tile-sorted position 0 "as if" it belonged to digit d's run
+        sm.global[d] = sm.dst[d] + 4ull * prefix - 4ull * start;  // (only thread d ever touches sm.global[d] / sm.dst[d] up to here)
     }
     __syncthreads();
 
@@ -427,15 +485,8 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
         const int p = i * SORT_THREADS + tid;
         if (FULL || p < tile_n) {
             const uint32_t k = sm.keys[p];
-            const unsigned d = digit_of(k);
-            const unsigned long long o = sm.global[d] + p;
-            if (MULTI) {
-                reinterpret_cast<uint32_t *>(__ldg(multi.table + d))[o] = k;
-                reinterpret_cast<uint8_t *>(__ldg(multi.table + RADIX + d))[o] = sm.vals[p];
-            } else {
-                keys_out[o] = k;
-                vals_out[o] = sm.vals[p];
-            }
+            const unsigned d = DIG ? (unsigned)sm.dig[p] : digit_of(k);
+            *reinterpret_cast<uint32_t *>(sm.global[d] + 4ull * (unsigned)p) = k;
         }
     }
 }
@@ -443,23 +494,70 @@ __device__ __forceinline__ void sweep_tile(SweepSmem &sm, const uint32_t *__rest
 #ifndef SORT_CTAS_PER_SM
 #define SORT_CTAS_PER_SM 4
 #endif
-template <typename DigitFn, bool MULTI = false>
+// One pass over both segments of the plan.  Tiles are numbered in START order (atomic ticket), so the look-back only
+// ever waits on tiles that are already running.
 __global__ void __launch_bounds__(SORT_THREADS, SORT_CTAS_PER_SM)
-onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out,
-                     const uint8_t *__restrict__ vals_in, uint8_t *__restrict__ vals_out, long long n,
-                     const unsigned long long *__restrict__ bin_base, unsigned long long *tile_status,
-                     unsigned *tile_counter, DigitFn digit_of, MultiDst multi = MultiDst{nullptr}) {
-    __shared__ SweepSmem sm;
+onesweep_pass_kernel(const SortPlan *__restrict__ plan, int pass, const unsigned long long *__restrict__ hist_all,
+                     unsigned long long *tile_status, unsigned *tile_counter) {
+    __shared__ SweepSmem<false> sm;
     const unsigned tid = threadIdx.x;
-    if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);   // tiles are numbered in start order: the
-#pragma unroll                                           // look-back only waits on tiles already running
+    if (tid == 0) {
+        const unsigned t = atomicAdd(tile_counter, 1u);
+        const unsigned s = t >= plan->seg[1].tile0 ? 1u : 0u;
+        const SortSeg sg = plan->seg[s];
+        const unsigned sel = plan->sel[s][pass];
+        sm.tile = t - sg.tile0;
+        sm.seg = s;
+        sm.skip = (t >= plan->total_tiles) || sel == 2;
+        sm.in = sel == 0 ? sg.x : sg.y;
+        sm.out = (unsigned long long)(uintptr_t)(sel == 0 ? sg.y : sg.x);
+        sm.n = sg.n;
+        sm.status = tile_status + (size_t)sg.tile0 * RADIX;
+    }
+#pragma unroll
     for (int w = 0; w < SORT_WARPS; w++) sm.warp_hist[w][tid] = 0;
     __syncthreads();
-    const unsigned tile = sm.tile;
-    if ((long long)(tile + 1) * SORT_TILE <= n)
-        sweep_tile<DigitFn, true, MULTI>(sm, keys_in, keys_out, vals_in, vals_out, n, bin_base, tile_status, digit_of, tile, multi);
+    if (sm.skip) return;
+    sm.dst[tid] = sm.out + 4ull * __ldg(hist_all + (sm.seg * 4 + pass) * RADIX + tid);
+    const ShiftDigit dg{8 * pass};
+    if ((long long)(sm.tile + 1) * SORT_TILE <= sm.n)
+        sweep_tile<ShiftDigit, true, false>(sm, RADIX, RADIX, dg);
     else
-        sweep_tile<DigitFn, false, MULTI>(sm, keys_in, keys_out, vals_in, vals_out, n, bin_base, tile_status, digit_of, tile, multi);
+        sweep_tile<ShiftDigit, false, false>(sm, RADIX, RADIX, dg);
+}
+
+// a segment whose last executed pass wrote into the alternate buffer is copied back (odd number of live passes)
+__global__ void __launch_bounds__(256)
+sort_copy_back_kernel(const SortPlan *__restrict__ plan) {
+    for (int s = 0; s < 2; s++) {
+        if (!plan->copy_back[s]) continue;
+        const SortSeg sg = plan->seg[s];
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += (long long)gridDim.x * blockDim.x)
+            sg.x[i] = sg.y[i];
+    }
+}
+
+// Multi-GPU exchange, local half: stable partition by key range where bucket d is stored at byte address table[d]
+// (+ this rank's running offset inside the bucket) -- typically inside rank d's peer-mapped receive buffer, so the
+// stores travel over NVLink and neither a staging copy nor an all-to-all is needed.
+__global__ void __launch_bounds__(SORT_THREADS, 3)
+partition_scatter_kernel(const uint32_t *__restrict__ keys, long long n, const uint32_t *__restrict__ splitters, int nspl,
+                         int steps, const unsigned long long *__restrict__ table, unsigned long long *tile_status,
+                         int sstride, unsigned *tile_counter) {
+    __shared__ SweepSmem<true> sm;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) { sm.tile = atomicAdd(tile_counter, 1u); sm.status = tile_status; sm.in = keys; sm.n = n; }
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) sm.warp_hist[w][tid] = 0;
+    if ((int)tid < nspl) sm.spl[tid] = __ldg(splitters + tid);
+    const int nd = nspl + 1;
+    sm.dst[tid] = ((int)tid < nd) ? __ldg(table + tid) : 0ull;
+    __syncthreads();
+    const SplitterDigit dg{sm.spl, nspl, steps};
+    if ((long long)(sm.tile + 1) * SORT_TILE <= n)
+        sweep_tile<SplitterDigit, true, true>(sm, sstride, nd, dg);
+    else
+        sweep_tile<SplitterDigit, false, true>(sm, sstride, nd, dg);
 }
 
 // top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536).
@@ -558,7 +656,8 @@ keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift,
     }
 }
 
-// test hook: MSS_HIST_EPOCH=<chunks> shortens the counter-fold period so small inputs exercise it
+// test hooks: MSS_HIST_EPOCH=<chunks> shortens the counter-fold period so small inputs exercise it;
+// MSS_SORT_NOSKIP=1 disables the single-bin pass skip (A/B timing, parity cross-check)
 static int hist_epoch_chunks() {
     static const int v = [] {
         const char *e = getenv("MSS_HIST_EPOCH");
@@ -567,79 +666,112 @@ static int hist_epoch_chunks() {
     }();
     return v;
 }
+static int sort_allow_skip() {
+    static const int v = [] {
+        const char *e = getenv("MSS_SORT_NOSKIP");
+        return (e && atoi(e)) ? 0 : 1;
+    }();
+    return v;
+}
 
 static size_t sort_tiles(int64_t n) { return (size_t)((n + SORT_TILE - 1) / SORT_TILE); }
 
+// kernels that opt into > 48 KB of dynamic shared memory: the attribute is per DEVICE, so it is (cheaply) set before
+// every launch instead of once per process (a process may touch a second GPU)
+static cudaError_t opt_in_smem() {
+    cudaError_t e = cudaFuncSetAttribute(radix_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(keys_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KH_SMEM);
+}
+
 struct SortWs {
-    uint32_t *keys_alt;
-    uint8_t *vals_alt;
-    unsigned long long *hist;      // [4][256]
+    uint32_t *alt;                 // [n_upper + 8]
+    SortPlan *plan;
+    unsigned long long *hist;      // [2][4][256]
     unsigned *counters;            // [4] (+pad)
-    unsigned long long *status;    // [4][tiles][256]
+    unsigned long long *status;    // [4][tiles_upper][256]
     size_t zero_bytes;             // hist..status are contiguous: one memset
     char *zero_base;
+    size_t tiles_upper;
 };
 
-static bool carve_sort(void *ws, size_t bytes, int64_t n, int passes, SortWs &o) {
+static bool carve_sort(void *ws, size_t bytes, int64_t n_upper, SortWs &o) {
     Carver c(ws, bytes);
-    o.keys_alt = c.take<uint32_t>((size_t)n);
-    o.vals_alt = c.take<uint8_t>((size_t)n);
-    o.hist = c.take<unsigned long long>(4 * RADIX);
+    o.tiles_upper = sort_tiles(n_upper) + 2;           // two segments: up to one partial tile each
+    o.alt = c.take<uint32_t>((size_t)n_upper + 8);
+    o.plan = c.take<SortPlan>(1);
+    o.hist = c.take<unsigned long long>(2 * 4 * RADIX);
     o.zero_base = (char *)o.hist;
     o.counters = c.take<unsigned>(64);
-    o.status = c.take<unsigned long long>((size_t)passes * sort_tiles(n) * RADIX);
-    o.zero_bytes = (size_t)((char *)(o.status + (size_t)passes * sort_tiles(n) * RADIX) - o.zero_base);
+    o.status = c.take<unsigned long long>(4 * o.tiles_upper * RADIX);
+    o.zero_bytes = (size_t)((char *)(o.status + 4 * o.tiles_upper * RADIX) - o.zero_base);
     return c.ok();
+}
+
+size_t sort_ws_bytes(int64_t n_upper) {
+    if (n_upper < 0) n_upper = 0;
+    return align_up(((size_t)n_upper + 8) * 4, 256) + 256 + 2 * 4 * RADIX * 8 + 256 + 256 +
+           4 * (sort_tiles(n_upper) + 2) * RADIX * 8 + 2048;
+}
+
+int sort_enqueue(const mss_eval_buffers *ev, uint32_t *xa, int64_t na, uint32_t *xb, int64_t nb, int64_t n_upper,
+                 void *ws, size_t ws_bytes, cudaStream_t st, const SortPlan **plan_dev) {
+    SortWs w;
+    if (!carve_sort(ws, ws_bytes, n_upper, w)) {
+        set_error("sort: workspace too small (%zu < %zu)", ws_bytes, sort_ws_bytes(n_upper));
+        return MSS_ERR_WORKSPACE;
+    }
+    MSS_REQUIRE(w.tiles_upper < (1ull << 31), "sort: n too large");
+    MSS_CHECK_CUDA(cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, st));
+    if (ev)
+        sort_plan_kernel<<<1, 1, 0, st>>>(w.plan, nullptr, nullptr, 0, nullptr, nullptr, 0, (const EvalState *)ev->state,
+                                          ev->keys, w.alt, ev->capacity);
+    else
+        sort_plan_kernel<<<1, 1, 0, st>>>(w.plan, xa, w.alt, na, xb, w.alt + ((na + 3) & ~3ll), nb, nullptr, nullptr,
+                                          nullptr, 0);
+    MSS_CHECK_LAUNCH();
+    if (plan_dev) *plan_dev = w.plan;
+    if (n_upper <= 0) return MSS_OK;
+    MSS_CHECK_CUDA(opt_in_smem());
+    // one CTA per SM and segment (192 KB of private counters each); a segment uses only the CTAs it has chunks for
+    const int hgrid = (int)std::max<long long>(1, std::min<long long>((n_upper + 4 * HIST_CHUNK_KEYS - 1) / (4 * HIST_CHUNK_KEYS),
+                                                                      (long long)sm_count()));
+    radix_histogram_kernel<<<dim3(hgrid, 2), HIST_THREADS, HIST_SMEM, st>>>(w.plan, w.hist, hist_epoch_chunks());
+    MSS_CHECK_LAUNCH();
+    radix_scan_bins_kernel<<<1, RADIX, 0, st>>>(w.hist, w.plan, sort_allow_skip());
+    MSS_CHECK_LAUNCH();
+    for (int p = 0; p < 4; p++) {
+        onesweep_pass_kernel<<<(unsigned)w.tiles_upper, SORT_THREADS, 0, st>>>(
+            w.plan, p, w.hist, w.status + (size_t)p * w.tiles_upper * RADIX, w.counters + p);
+        MSS_CHECK_LAUNCH();
+    }
+    const int cgrid = (int)std::min<long long>((n_upper + 1023) / 1024, (long long)sm_count() * 8);
+    sort_copy_back_kernel<<<std::max(cgrid, 1), 256, 0, st>>>(w.plan);
+    MSS_CHECK_LAUNCH();
+    return MSS_OK;
+}
+
+int plan_enqueue(SortPlan *plan_dev, const uint32_t *xa, int64_t na, const uint32_t *xb, int64_t nb, cudaStream_t st) {
+    sort_plan_kernel<<<1, 1, 0, st>>>(plan_dev, const_cast<uint32_t *>(xa), nullptr, na, const_cast<uint32_t *>(xb), nullptr, nb,
+                                      nullptr, nullptr, nullptr, 0);
+    MSS_CHECK_LAUNCH();
+    return MSS_OK;
 }
 
 }  // namespace mss
 
 using namespace mss;
 
-extern "C" size_t mss_sort_pairs_workspace_bytes(int64_t n) {
-    if (n < 0) n = 0;
-    return align_up((size_t)n * 4, 256) + align_up((size_t)n, 256) + 4 * RADIX * 8 + 256 + 256 +
-           4 * sort_tiles(n) * RADIX * 8 + 2048;
-}
+extern "C" size_t mss_sort_keys_workspace_bytes(int64_t n_total) { return sort_ws_bytes(n_total); }
 
-extern "C" int mss_sort_pairs(uint32_t *keys, uint8_t *labs, int64_t n, void *workspace, size_t workspace_bytes,
-                              void *stream) {
-    MSS_REQUIRE(n >= 0, "mss_sort_pairs: n < 0");
-    if (n <= 1) return MSS_OK;
-    MSS_REQUIRE(keys && labs && workspace, "mss_sort_pairs: null pointer");
-    SortWs w;
-    if (!carve_sort(workspace, workspace_bytes, n, 4, w)) {
-        set_error("mss_sort_pairs: workspace too small (%zu < %zu)", workspace_bytes, mss_sort_pairs_workspace_bytes(n));
-        return MSS_ERR_WORKSPACE;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    MSS_CHECK_CUDA(cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, st));
-    const size_t tiles = sort_tiles(n);
-    MSS_REQUIRE(tiles < (1ull << 31), "mss_sort_pairs: n too large");
-    MSS_REQUIRE(((uintptr_t)keys & 3) == 0, "mss_sort_pairs: keys must be 4-byte aligned");
-    static std::atomic<bool> hist_attr{false};
-    if (!hist_attr.load()) {
-        MSS_CHECK_CUDA(cudaFuncSetAttribute(radix_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_SMEM));
-        hist_attr.store(true);
-    }
-    // one CTA per SM (192 KB of private counters each); small inputs use fewer CTAs (>= 4 chunks per CTA)
-    int hgrid = (int)std::max<long long>(1, std::min<long long>((n + 4 * HIST_CHUNK_KEYS - 1) / (4 * HIST_CHUNK_KEYS),
-                                                                (long long)sm_count()));
-    radix_histogram_kernel<<<hgrid, HIST_THREADS, HIST_SMEM, st>>>(keys, n, w.hist, hist_epoch_chunks());
-    MSS_CHECK_LAUNCH();
-    radix_scan_bins_kernel<<<1, RADIX, 0, st>>>(w.hist, 4);
-    MSS_CHECK_LAUNCH();
-    uint32_t *kin = keys, *kout = w.keys_alt;
-    uint8_t *vin = labs, *vout = w.vals_alt;
-    for (int p = 0; p < 4; p++) {
-        onesweep_pass_kernel<ShiftDigit><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
-            kin, kout, vin, vout, n, w.hist + p * RADIX, w.status + (size_t)p * tiles * RADIX, w.counters + p,
-            ShiftDigit{8 * p});
-        MSS_CHECK_LAUNCH();
-        std::swap(kin, kout);
-        std::swap(vin, vout);
-    }
-    return MSS_OK;   // 4 passes: the result is back in (keys, labs)
+extern "C" int mss_sort_keys(uint32_t *keys_a, int64_t n_a, uint32_t *keys_b, int64_t n_b, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+    MSS_REQUIRE(n_a >= 0 && n_b >= 0, "mss_sort_keys: negative size");
+    if (n_a + n_b == 0) return MSS_OK;
+    MSS_REQUIRE((n_a == 0 || keys_a) && (n_b == 0 || keys_b) && workspace, "mss_sort_keys: null pointer");
+    MSS_REQUIRE((((uintptr_t)keys_a | (uintptr_t)keys_b) & 3) == 0, "mss_sort_keys: keys must be 4-byte aligned");
+    return sort_enqueue(nullptr, keys_a, n_a, keys_b, n_b, n_a + n_b, workspace, workspace_bytes, (cudaStream_t)stream,
+                        nullptr);
 }
 
 static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist, void *stream);
@@ -661,11 +793,7 @@ static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, 
     MSS_CHECK_CUDA(cudaMemsetAsync(hist, 0, sizeof(int64_t) << bits, st));
     if (n == 0) return MSS_OK;
     MSS_REQUIRE(keys, "mss_keys_histogram: null keys");
-    static std::atomic<bool> kh_attr{false};
-    if (!kh_attr.load()) {
-        MSS_CHECK_CUDA(cudaFuncSetAttribute(keys_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KH_SMEM));
-        kh_attr.store(true);
-    }
+    MSS_CHECK_CUDA(opt_in_smem());
     // one CTA per SM (128 KB window each); small inputs use fewer CTAs (>= 16 K keys per CTA)
     int grid = (int)std::max<long long>(1, std::min<long long>((n / every + 16383) / 16384, (long long)sm_count()));
     keys_histogram_kernel<<<grid, KH_THREADS, KH_SMEM, st>>>(keys, n, 32 - bits, 1u << bits, every, (unsigned long long *)hist);
@@ -673,53 +801,32 @@ static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, 
     return MSS_OK;
 }
 
-extern "C" size_t mss_partition_workspace_bytes(int64_t n) {
+// ---- key-range partition (multi-GPU exchange) --------------------------------------------------------------
+static int status_stride(int parts) { return (parts + 15) / 16 * 16; }
+
+extern "C" size_t mss_partition_workspace_bytes(int64_t n, int parts) {
     if (n < 0) n = 0;
-    return 3 * RADIX * 8 + 256 + 256 + 2 * sort_tiles(n) * RADIX * 8 + 4096;
+    if (parts < 1) parts = 1;
+    return 3 * RADIX * 8 + 256 + 256 + (sort_tiles(n) + 1) * (size_t)status_stride(parts) * 8 + 4096;
 }
 
-// exclusive prefix of the bucket sizes
-__global__ void __launch_bounds__(RADIX)
-partition_bases_kernel(const unsigned long long *counts, unsigned long long *base) {
-    __shared__ unsigned long long sh[RADIX];
-    sh[threadIdx.x] = counts[threadIdx.x];
-    __syncthreads();
-    unsigned long long b = 0;
-    for (int j = 0; j < (int)threadIdx.x; j++) b += sh[j];
-    base[threadIdx.x] = b;
-}
-
-__global__ void __launch_bounds__(256)
-partition_count_tiles_kernel(const uint32_t *__restrict__ keys, long long n, SplitterDigit dg,
-                             unsigned long long *__restrict__ counts) {
-    __shared__ unsigned s_c[RADIX];
-    s_c[threadIdx.x] = 0;
-    __syncthreads();
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        atomicAdd(&s_c[dg(__ldg(keys + i))], 1u);
-    __syncthreads();
-    if (s_c[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_c[threadIdx.x]);
-}
-
-// parts <= 16 (one destination per GPU of a box): lane-private counters, no atomics in the loop.  The atomic
-// version above serialises 32-way when almost every key of a warp goes to the same destination.
+// parts <= 16 (one destination per GPU of a box): lane-private counters, no atomics in the loop (shared-memory atomics
+// serialise 32-way when almost every key of a warp goes to the same destination); more parts: shared atomics.
 constexpr int PC_SMALL = 16;
 __global__ void __launch_bounds__(256)
-partition_count_small_kernel(const uint32_t *__restrict__ keys, long long n, SplitterDigit dg,
-                             unsigned long long *__restrict__ counts) {
+partition_count_kernel(const uint32_t *__restrict__ keys, long long n, const uint32_t *__restrict__ splitters, int nspl,
+                       int steps, unsigned long long *__restrict__ counts) {
     __shared__ unsigned s_c[PC_SMALL * 256];
-    __shared__ uint32_t s_spl[PC_SMALL];
-#pragma unroll
-    for (int p = 0; p < PC_SMALL; p++) s_c[p * 256 + threadIdx.x] = 0;
-    if (threadIdx.x < PC_SMALL) s_spl[threadIdx.x] = ((int)threadIdx.x < dg.nspl) ? dg.spl[threadIdx.x] : 0xFFFFFFFFu;
+    __shared__ uint32_t s_spl[RADIX];
+    const bool small = nspl < PC_SMALL;
+    for (int i = threadIdx.x; i < PC_SMALL * 256; i += 256) s_c[i] = 0;
+    if ((int)threadIdx.x < nspl) s_spl[threadIdx.x] = __ldg(splitters + threadIdx.x);
     __syncthreads();
-    const int nspl = dg.nspl;
+    const SplitterDigit dg{s_spl, nspl, steps};
     auto tally = [&](uint32_t k) {
-        unsigned d = 0;
-#pragma unroll
-        for (int j = 0; j < PC_SMALL - 1; j++) d += (j < nspl && k >= s_spl[j]);   // dest = #{j : key >= spl[j]}
-        s_c[d * 256 + threadIdx.x]++;
+        const unsigned d = dg(k);
+        if (small) s_c[d * 256 + threadIdx.x]++;
+        else atomicAdd(&s_c[d], 1u);
     };
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long head = min(n, (long long)(((16 - ((uintptr_t)keys & 15)) & 15) >> 2));
@@ -742,22 +849,27 @@ partition_count_small_kernel(const uint32_t *__restrict__ keys, long long n, Spl
             tally(__ldg(keys + i));
         }
     __syncthreads();
-    // warp w sums destinations w, w + 8
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int p = warp; p < PC_SMALL; p += 8) {
-        unsigned long long acc = 0;
-        for (int t = lane; t < 256; t += 32) acc += s_c[p * 256 + t];
+    if (small) {
+        // warp w sums destinations w, w + 8
+        const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int p = warp; p < PC_SMALL; p += 8) {
+            unsigned long long acc = 0;
+            for (int t = lane; t < 256; t += 32) acc += s_c[p * 256 + t];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0 && acc) atomicAdd(counts + p, acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0 && acc) atomicAdd(counts + p, acc);
+        }
+    } else if (s_c[threadIdx.x]) {
+        atomicAdd(counts + threadIdx.x, (unsigned long long)s_c[threadIdx.x]);
     }
 }
 
-static void launch_partition_count(const uint32_t *keys, int64_t n, SplitterDigit dg, int parts,
-                                   unsigned long long *counts, cudaStream_t st) {
-    int grid = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 8);
-    if (parts <= PC_SMALL) partition_count_small_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
-    else partition_count_tiles_kernel<<<grid, 256, 0, st>>>(keys, n, dg, counts);
+static int count_into(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts, unsigned long long *counts,
+                      cudaStream_t st) {
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n + 2047) / 2048, (long long)sm_count() * 8));
+    partition_count_kernel<<<grid, 256, 0, st>>>(keys, n, splitters, parts - 1, splitter_steps(parts), counts);
+    MSS_CHECK_LAUNCH();
+    return MSS_OK;
 }
 
 extern "C" int mss_partition_count(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
@@ -770,8 +882,8 @@ extern "C" int mss_partition_count(const uint32_t *keys, int64_t n, const uint32
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *counts = (unsigned long long *)workspace;
     MSS_CHECK_CUDA(cudaMemsetAsync(counts, 0, RADIX * 8, st));
-    launch_partition_count(keys, n, SplitterDigit{splitters, parts - 1}, parts, counts, st);
-    MSS_CHECK_LAUNCH();
+    int rc = count_into(keys, n, splitters, parts, counts, st);
+    if (rc) return rc;
     unsigned long long h[RADIX];
     MSS_CHECK_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, st));
     MSS_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -779,77 +891,70 @@ extern "C" int mss_partition_count(const uint32_t *keys, int64_t n, const uint32
     return MSS_OK;
 }
 
-extern "C" int mss_partition_scatter_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n,
-                                           const uint32_t *splitters, int parts, const uint64_t *dst_keys_host,
-                                           const uint64_t *dst_labs_host, const int64_t *dst_offsets_host,
-                                           void *workspace, size_t workspace_bytes, void *stream) {
-    MSS_REQUIRE(parts >= 1 && parts <= RADIX, "mss_partition_scatter_pairs: parts must be 1..256");
-    MSS_REQUIRE(n >= 0 && dst_keys_host && dst_labs_host && dst_offsets_host, "mss_partition_scatter_pairs: bad arguments");
-    if (n == 0) return MSS_OK;
-    MSS_REQUIRE(keys && labs && workspace && (parts == 1 || splitters), "mss_partition_scatter_pairs: null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
+// bucket d -> byte address table_host[d]; status / counter / device table carved from the workspace
+static int scatter_to(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
+                      const unsigned long long *table_host, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                      const char *who) {
     const size_t tiles = sort_tiles(n);
+    const int sstride = status_stride(parts);
     Carver c(workspace, workspace_bytes);
-    unsigned long long *base = c.take<unsigned long long>(RADIX);          // element offset of this rank's block in bucket d
-    unsigned long long *table = c.take<unsigned long long>(2 * RADIX);     // destination base addresses
+    unsigned long long *table = c.take<unsigned long long>(RADIX);
     unsigned *counter = c.take<unsigned>(64);
-    unsigned long long *status = c.take<unsigned long long>(tiles * RADIX);
+    unsigned long long *status = c.take<unsigned long long>(tiles * sstride);
     if (!c.ok()) {
-        set_error("mss_partition_scatter_pairs: workspace too small (%zu < %zu)", workspace_bytes, mss_partition_workspace_bytes(n));
+        set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, mss_partition_workspace_bytes(n, parts));
         return MSS_ERR_WORKSPACE;
     }
-    unsigned long long h[3 * RADIX];
-    for (int j = 0; j < RADIX; j++) {
-        h[j] = (j < parts) ? (unsigned long long)dst_offsets_host[j] : 0ull;
-        h[RADIX + j] = (j < parts) ? (unsigned long long)dst_keys_host[j] : 0ull;
-        h[2 * RADIX + j] = (j < parts) ? (unsigned long long)dst_labs_host[j] : 0ull;
-        if (j < parts) MSS_REQUIRE(dst_keys_host[j] && dst_labs_host[j] && dst_offsets_host[j] >= 0, "mss_partition_scatter_pairs: bad destination %d", j);
-    }
-    MSS_CHECK_CUDA(cudaMemsetAsync(counter, 0, (size_t)((char *)(status + tiles * RADIX) - (char *)counter), st));
-    // base and table are adjacent in the carve (both 256-byte aligned, RADIX * 8 = 2048 bytes): one copy
-    MSS_REQUIRE((char *)table == (char *)base + RADIX * 8, "mss_partition_scatter_pairs: internal layout");
-    MSS_CHECK_CUDA(cudaMemcpyAsync(base, h, sizeof(h), cudaMemcpyHostToDevice, st));
-    SplitterDigit dg{splitters, parts - 1};
-    onesweep_pass_kernel<SplitterDigit, true><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
-        keys, nullptr, labs, nullptr, n, base, status, counter, dg, MultiDst{table});
+    MSS_REQUIRE(tiles < (1ull << 31), "%s: n too large", who);
+    MSS_CHECK_CUDA(cudaMemsetAsync(counter, 0, (size_t)((char *)(status + tiles * sstride) - (char *)counter), st));
+    MSS_CHECK_CUDA(cudaMemcpyAsync(table, table_host, (size_t)parts * 8, cudaMemcpyHostToDevice, st));
+    partition_scatter_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(keys, n, splitters, parts - 1, splitter_steps(parts),
+                                                                      table, status, sstride, counter);
     MSS_CHECK_LAUNCH();
-    // the host staging array must outlive the async copy
-    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
     return MSS_OK;
 }
 
-extern "C" int mss_partition_pairs(const uint32_t *keys, const uint8_t *labs, int64_t n, const uint32_t *splitters,
-                                   int parts, uint32_t *keys_out, uint8_t *labs_out, int64_t *out_counts_host,
-                                   void *workspace, size_t workspace_bytes, void *stream) {
-    MSS_REQUIRE(parts >= 1 && parts <= RADIX, "mss_partition_pairs: parts must be 1..256");
-    MSS_REQUIRE(n >= 0 && out_counts_host, "mss_partition_pairs: bad arguments");
+extern "C" int mss_partition_scatter_keys(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
+                                          const uint64_t *dst_keys_host, const int64_t *dst_offsets_host, void *workspace,
+                                          size_t workspace_bytes, void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= RADIX, "mss_partition_scatter_keys: parts must be 1..256");
+    MSS_REQUIRE(n >= 0 && dst_keys_host && dst_offsets_host, "mss_partition_scatter_keys: bad arguments");
+    if (n == 0) return MSS_OK;
+    MSS_REQUIRE(keys && workspace && (parts == 1 || splitters), "mss_partition_scatter_keys: null pointer");
+    unsigned long long h[RADIX];
+    for (int j = 0; j < parts; j++) {
+        MSS_REQUIRE(dst_keys_host[j] && dst_offsets_host[j] >= 0 && (dst_keys_host[j] & 3) == 0,
+                    "mss_partition_scatter_keys: bad destination %d", j);
+        h[j] = (unsigned long long)dst_keys_host[j] + 4ull * (unsigned long long)dst_offsets_host[j];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = scatter_to(keys, n, splitters, parts, h, workspace, workspace_bytes, st, "mss_partition_scatter_keys");
+    if (rc) return rc;
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));     // the host staging array must outlive the async copy
+    return MSS_OK;
+}
+
+extern "C" int mss_partition_keys(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
+                                  uint32_t *keys_out, int64_t *out_counts_host, void *workspace, size_t workspace_bytes,
+                                  void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= RADIX, "mss_partition_keys: parts must be 1..256");
+    MSS_REQUIRE(n >= 0 && out_counts_host, "mss_partition_keys: bad arguments");
     for (int j = 0; j < parts; j++) out_counts_host[j] = 0;
     if (n == 0) return MSS_OK;
-    MSS_REQUIRE(keys && labs && keys_out && labs_out && workspace && (parts == 1 || splitters),
-                "mss_partition_pairs: null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t tiles = sort_tiles(n);
-    Carver c(workspace, workspace_bytes);
-    unsigned long long *base = c.take<unsigned long long>(RADIX);
-    unsigned long long *counts = c.take<unsigned long long>(RADIX);
-    unsigned *counter = c.take<unsigned>(64);
-    unsigned long long *status = c.take<unsigned long long>(tiles * RADIX);
-    if (!c.ok()) {
-        set_error("mss_partition_pairs: workspace too small (%zu < %zu)", workspace_bytes, mss_partition_workspace_bytes(n));
-        return MSS_ERR_WORKSPACE;
+    MSS_REQUIRE(keys && keys_out && workspace && (parts == 1 || splitters), "mss_partition_keys: null pointer");
+    MSS_REQUIRE(workspace_bytes >= mss_partition_workspace_bytes(n, parts), "mss_partition_keys: workspace too small");
+    // the last 2 KB of the workspace hold the counts (scatter_to carves from the front)
+    const size_t front = (workspace_bytes - 2048) & ~(size_t)255;
+    int rc = mss_partition_count(keys, n, splitters, parts, out_counts_host, (char *)workspace + front, 2048, stream);
+    if (rc) return rc;
+    unsigned long long h[RADIX], run = 0;
+    for (int j = 0; j < parts; j++) {
+        h[j] = (unsigned long long)(uintptr_t)keys_out + 4ull * run;
+        run += (unsigned long long)out_counts_host[j];
     }
-    MSS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)((char *)(status + tiles * RADIX) - (char *)workspace), st));
-    SplitterDigit dg{splitters, parts - 1};
-    launch_partition_count(keys, n, dg, parts, counts, st);
-    MSS_CHECK_LAUNCH();
-    partition_bases_kernel<<<1, RADIX, 0, st>>>(counts, base);
-    MSS_CHECK_LAUNCH();
-    onesweep_pass_kernel<SplitterDigit><<<(unsigned)tiles, SORT_THREADS, 0, st>>>(
-        keys, keys_out, labs, labs_out, n, base, status, counter, dg);
-    MSS_CHECK_LAUNCH();
-    unsigned long long h[RADIX];
-    MSS_CHECK_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, st));
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = scatter_to(keys, n, splitters, parts, h, workspace, front, st, "mss_partition_keys");
+    if (rc) return rc;
     MSS_CHECK_CUDA(cudaStreamSynchronize(st));
-    for (int j = 0; j < parts; j++) out_counts_host[j] = (int64_t)h[j];
     return MSS_OK;
 }

@@ -183,8 +183,8 @@ eval_append_kernel(const float *__restrict__ scores, const void *__restrict__ la
 }
 
 static EvalDev to_dev(const mss_eval_buffers *ev) {
-    EvalDev d{nullptr, nullptr, nullptr, 0};
-    if (ev) { d.keys = ev->keys; d.labs = ev->labs; d.state = (EvalState *)ev->state; d.capacity = ev->capacity; }
+    EvalDev d{nullptr, nullptr, 0};
+    if (ev) { d.keys = ev->keys; d.state = (EvalState *)ev->state; d.capacity = ev->capacity; }
     return d;
 }
 
@@ -205,11 +205,11 @@ extern "C" int mss_eval_state_host(const mss_eval_buffers *ev, int64_t out_host[
     EvalState h;
     MSS_CHECK_CUDA(cudaMemcpyAsync(&h, ev->state, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     MSS_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    out_host[0] = (int64_t)h.count; out_host[1] = (int64_t)h.n_pos;
+    out_host[0] = (int64_t)(h.n_neg + h.n_pos); out_host[1] = (int64_t)h.n_pos;
     out_host[2] = h.nan_flag; out_host[3] = h.inf_flag;
-    if (h.overflow || (int64_t)h.count > ev->capacity) {
+    if (h.overflow || (int64_t)(h.n_neg + h.n_pos) > ev->capacity) {       // the two streams met (or a CTA was dropped)
         set_error("evaluator capacity %lld exceeded (%llu valid pixels appended)", (long long)ev->capacity,
-                  (unsigned long long)h.count);
+                  (unsigned long long)(h.n_neg + h.n_pos + h.overflow));
         return MSS_ERR_WORKSPACE;
     }
     return MSS_OK;
@@ -217,7 +217,7 @@ extern "C" int mss_eval_state_host(const mss_eval_buffers *ev, int64_t out_host[
 
 extern "C" int mss_eval_append(const float *scores, const void *labels, int label_dtype, int64_t n,
                                int64_t id_in, int64_t id_out, const mss_eval_buffers *ev, void *stream) {
-    MSS_REQUIRE(ev && ev->keys && ev->labs && ev->state, "mss_eval_append: null evaluator buffers");
+    MSS_REQUIRE(ev && ev->keys && ev->state, "mss_eval_append: null evaluator buffers");
     MSS_REQUIRE(n >= 0, "mss_eval_append: n < 0");
     MSS_REQUIRE(label_dtype == MSS_LABEL_U8 || label_dtype == MSS_LABEL_I32 || label_dtype == MSS_LABEL_I64,
                 "mss_eval_append: bad label_dtype %d", label_dtype);
@@ -248,7 +248,7 @@ extern "C" int mss_deeplab_score(const float *logits, int64_t B, int C, int64_t 
     const bool emit = ev != nullptr;
     if (emit) {
         MSS_REQUIRE(labels, "mss_deeplab_score: evaluator given without labels");
-        MSS_REQUIRE(ev->keys && ev->labs && ev->state, "mss_deeplab_score: null evaluator buffers");
+        MSS_REQUIRE(ev->keys && ev->state, "mss_deeplab_score: null evaluator buffers");
         MSS_REQUIRE(key_which && (key_which & (key_which - 1)) == 0 && (key_which & which),
                     "mss_deeplab_score: key_which must be exactly one of the selected scores");
         MSS_REQUIRE(label_dtype == MSS_LABEL_U8 || label_dtype == MSS_LABEL_I32 || label_dtype == MSS_LABEL_I64,

@@ -36,6 +36,7 @@ def score_maps(logit: torch.Tensor, which: Iterable[str] = ("energy",), *, label
     named ``key`` is also appended -- for pixels labelled ``id_in`` / ``id_out`` only -- to the on-device
     evaluator inside the same kernel (ignore-label masking fused into scoring).
     """
+    L.forbid_grad("deeplab.score_maps", logit)     # (the autograd Functions below call it with grad mode off)
     logit = _prep_logits(logit)
     which = tuple(which)
     mask = 0
@@ -204,8 +205,11 @@ def head_scores(feature: torch.Tensor, w_cls: torch.Tensor, w_ood: torch.Tensor,
                         (or the head-resolution energy [B, h, w] when ``size`` is None)
         dec2 (only with ``want_dec2``)
 
-    ``w_cls`` / ``w_ood`` are the weights of the two bias-free 1x1 convolutions ([C, K] or [C, K, 1, 1])."""
+    ``w_cls`` / ``w_ood`` are the weights of the two bias-free 1x1 convolutions ([C, K] or [C, K, 1, 1]).
+    Forward only: with autograd enabled and inputs that require grad it raises ``MssError`` (no backward kernel
+    for the head GEMM) instead of returning tensors without grad_fn -- use it under ``torch.no_grad()``."""
     L.require_cuda(feature, "feature")
+    L.forbid_grad("deeplab.head_scores (fused head GEMM)", feature, w_cls, w_ood)
     if feature.dim() != 4:
         raise ValueError("feature must be [B, K, h, w]")
     x = feature.float().contiguous()

@@ -62,8 +62,17 @@ class CudaBackend:
     def state(self, buf) -> Tuple[int, int, int, int]:
         return buf.read_state()
 
-    def pairs(self, buf, m):
-        return buf.keys[:m], buf.labs[:m]
+    def streams(self, buf, m, n_pos):
+        """-> (negative keys, positive keys) of the buffer."""
+        return buf.streams(m, n_pos)
+
+    def finish_local(self, buf, recall_level):
+        """Single-GPU result straight from the buffer (sort + counts + tail)."""
+        from .metric import _finish
+        return _finish(buf, recall_level)
+
+    def _spl(self, splitters):
+        return torch.from_numpy(np.asarray(list(splitters) + [0], dtype=np.uint32).view(np.int32)).to(self.device)
 
     # -- integer stages
     def histogram(self, keys: torch.Tensor, m: int, bits: int, every: int = 1) -> torch.Tensor:
@@ -74,25 +83,23 @@ class CudaBackend:
                                                         L.stream_ptr(self.device)), "mss_keys_histogram_sampled")
         return hist
 
-    def partition(self, keys, labs, m: int, splitters: Sequence[int], parts: int):
+    def partition(self, keys, m: int, splitters: Sequence[int], parts: int):
         import ctypes as C
         lib = L.load()
         keys_out = torch.empty(max(m, 1), dtype=torch.int32, device=self.device)
-        labs_out = torch.empty(max(m, 1), dtype=torch.uint8, device=self.device)
-        spl = torch.from_numpy(np.asarray(list(splitters) + [0], dtype=np.uint32).view(np.int32)).to(self.device)
+        spl = self._spl(splitters)
         counts = (C.c_int64 * parts)()
-        nbytes = lib.mss_partition_workspace_bytes(m)
+        nbytes = lib.mss_partition_workspace_bytes(m, parts)
         ws = L.workspace(nbytes, self.device)
         with torch.cuda.device(self.device):
-            L.check(lib.mss_partition_pairs(keys.data_ptr(), labs.data_ptr(), m, spl.data_ptr(), parts,
-                                            keys_out.data_ptr(), labs_out.data_ptr(), counts, ws.data_ptr(), nbytes,
-                                            L.stream_ptr(self.device)), "mss_partition_pairs")
-        return keys_out[:m], labs_out[:m], [int(c) for c in counts]
+            L.check(lib.mss_partition_keys(keys.data_ptr(), m, spl.data_ptr(), parts, keys_out.data_ptr(), counts,
+                                           ws.data_ptr(), nbytes, L.stream_ptr(self.device)), "mss_partition_keys")
+        return keys_out[:m], [int(c) for c in counts]
 
     def partition_count(self, keys, m: int, splitters: Sequence[int], parts: int) -> List[int]:
         import ctypes as C
         lib = L.load()
-        spl = torch.from_numpy(np.asarray(list(splitters) + [0], dtype=np.uint32).view(np.int32)).to(self.device)
+        spl = self._spl(splitters)
         counts = (C.c_int64 * parts)()
         ws = L.workspace(4096, self.device)
         with torch.cuda.device(self.device):
@@ -100,63 +107,48 @@ class CudaBackend:
                                             L.stream_ptr(self.device)), "mss_partition_count")
         return [int(c) for c in counts]
 
-    def partition_scatter(self, keys, labs, m: int, splitters: Sequence[int], parts: int, dst_keys: Sequence[int],
-                          dst_labs: Sequence[int], dst_offsets: Sequence[int]):
-        """Fused partition + exchange: bucket d is stored at element offset ``dst_offsets[d]`` of the buffers at
-        device addresses ``dst_keys[d]`` / ``dst_labs[d]`` (peer memory for d != this rank)."""
+    def partition_scatter(self, keys, m: int, splitters: Sequence[int], parts: int, dst_keys: Sequence[int],
+                          dst_offsets: Sequence[int]):
+        """Fused partition + exchange: bucket d is stored at element offset ``dst_offsets[d]`` of the uint32 buffer at
+        device address ``dst_keys[d]`` (peer memory for d != this rank)."""
         import ctypes as C
         lib = L.load()
-        spl = torch.from_numpy(np.asarray(list(splitters) + [0], dtype=np.uint32).view(np.int32)).to(self.device)
+        spl = self._spl(splitters)
         dk = (C.c_uint64 * parts)(*[int(x) for x in dst_keys])
-        dl = (C.c_uint64 * parts)(*[int(x) for x in dst_labs])
         do = (C.c_int64 * parts)(*[int(x) for x in dst_offsets])
-        nbytes = lib.mss_partition_workspace_bytes(m)
+        nbytes = lib.mss_partition_workspace_bytes(m, parts)
         ws = L.workspace(nbytes, self.device)
         with torch.cuda.device(self.device):
-            L.check(lib.mss_partition_scatter_pairs(keys.data_ptr(), labs.data_ptr(), m, spl.data_ptr(), parts, dk, dl, do,
-                                                    ws.data_ptr(), nbytes, L.stream_ptr(self.device)),
-                    "mss_partition_scatter_pairs")
+            L.check(lib.mss_partition_scatter_keys(keys.data_ptr(), m, spl.data_ptr(), parts, dk, do, ws.data_ptr(), nbytes,
+                                                   L.stream_ptr(self.device)), "mss_partition_scatter_keys")
 
     # -- peer-mapped receive buffers (torch symmetric memory: every rank can store into every rank's buffer)
-    def peer_buffers(self, capacity: int, group):
-        """-> (keys int32 [capacity], labs uint8 [capacity], key_ptrs[world], lab_ptrs[world], handle) or raises."""
+    def peer_alloc(self, capacity: int):
+        """Local half (may raise, e.g. out of memory): the symmetric allocation, not yet mapped by the peers."""
+        import torch.distributed._symmetric_memory as symm
+        return symm.empty(int(capacity) * 4, dtype=torch.uint8, device=self.device)
+
+    def peer_map(self, raw, capacity: int, group):
+        """Collective half: exchange the handles.  -> dict(keys int32 [capacity], key_ptrs[world], ...)."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
-        cap = int(capacity)
-        ck = (str(self.device), id(group))
-        cached = _PEER_CACHE.get(ck)
-        if cached is not None and cached["cap"] >= cap:
-            return cached
         grp = group if group is not None else dist.group.WORLD
         if tuple(int(x) for x in torch.__version__.split("+")[0].split(".")[:2]) < (2, 8):   # older torch: enable the group first
             try:
                 symm.enable_symm_mem_for_group(grp.group_name)
             except Exception:
                 pass
-        kb = (cap * 4 + 255) // 256 * 256
-        raw = symm.empty(kb + cap, dtype=torch.uint8, device=self.device)     # one allocation: [keys | labs]
         hdl = symm.rendezvous(raw, grp)
-        keys = raw[: cap * 4].view(torch.int32)
-        labs = raw[kb: kb + cap]
-        ptrs = [int(p) for p in hdl.buffer_ptrs]
-        _PEER_CACHE[ck] = {"cap": cap, "raw": raw, "hdl": hdl, "keys": keys, "labs": labs,
-                           "key_ptrs": ptrs, "lab_ptrs": [p + kb for p in ptrs]}
-        return _PEER_CACHE[ck]
+        return {"cap": int(capacity), "raw": raw, "hdl": hdl, "keys": raw.view(torch.int32),
+                "key_ptrs": [int(p) for p in hdl.buffer_ptrs]}
 
-    def sort(self, keys, labs, m: int):
-        from .metric import sort_pairs
-        sort_pairs(keys, labs, m)
+    def sort2(self, neg, n_neg: int, pos, n_pos: int):
+        from .metric import sort_keys
+        sort_keys(neg, n_neg, pos, n_pos)
 
-    def counts(self, keys, labs, m: int, pos_before: int, idx_before: int):
+    def counts(self, neg, n_neg: int, pos, n_pos: int, pos_before: int, neg_before: int):
         from .metric import counts_from_sorted
-        tps, fps, _, _ = counts_from_sorted(keys, labs, m, pos_before, idx_before)
-        return tps, fps
-
-    def counts_local(self, keys, labs, m: int):
-        """-> (tps, fps, #positives) of this slice alone (prefixes of earlier slices not included)."""
-        from .metric import counts_from_sorted
-        tps, fps, n_pos, _ = counts_from_sorted(keys, labs, m, 0, 0)
-        return tps, fps, n_pos
+        return counts_from_sorted(neg, n_neg, pos, n_pos, pos_before, neg_before)
 
     def tail(self, tps, fps, recall_level=0.95):
         from .metric import metrics_tail
@@ -227,16 +219,43 @@ class StreamingEvaluator:
     # ------------------------------------------------------------------ result
     def compute(self, recall_level: float = 0.95):
         be = self.backend
-        m, n_pos, nan, inf = be.state(self.buf)
         if not self.distributed:
-            if n_pos == 0 or n_pos == m:
-                return None
-            _raise_nonfinite(nan, inf)
-            keys, labs = be.pairs(self.buf, m)
-            be.sort(keys, labs, m)
-            tps, fps = be.counts(keys, labs, m, 0, 0)
-            return be.tail(tps, fps, recall_level)
+            return be.finish_local(self.buf, recall_level)
+        m, n_pos, nan, inf = be.state(self.buf)
         return self._compute_distributed(m, n_pos, nan, inf, recall_level)
+
+    def _peer_buffers(self, need: int, g):
+        """Peer-mapped receive buffer of >= need keys on every rank, or None (on EVERY rank) if it cannot be had.
+        Capability and the local allocation are agreed on with a cheap collective BEFORE the collective handle
+        exchange, so a rank that fails (no peer access, out of memory) cannot leave the others blocked in it."""
+        import torch.distributed as dist
+        be = self.backend
+        grp = g if g is not None else dist.group.WORLD
+        ck = (str(getattr(be, "device", "cpu")), getattr(grp, "group_name", None) or id(grp))
+        cached = _PEER_CACHE.get(ck)
+        # `need` comes from all-gathered counts and every rank has taken the same decisions before, so the cache state
+        # is the same everywhere; the MIN all-reduce makes that an agreement instead of an assumption
+        have = be.tensor([1 if (cached is not None and cached["cap"] >= need) else 0], torch.int64)
+        dist.all_reduce(have, op=dist.ReduceOp.MIN, group=g)
+        if int(have.item()) == 1:
+            return cached
+        cap = max(need + need // 8, 1 << 20)
+        raw, err = None, None
+        try:
+            raw = be.peer_alloc(cap)
+        except Exception as e:
+            err = repr(e)
+        ok = be.tensor([0 if raw is None else 1], torch.int64)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=g)
+        if int(ok.item()) != 1:
+            self.p2p_error = err or "a peer could not allocate its receive buffer"
+            return None
+        try:
+            _PEER_CACHE[ck] = be.peer_map(raw, cap, g)
+        except Exception as e:               # the handle exchange itself is collective: it fails (or not) everywhere
+            self.p2p_error = repr(e)
+            return None
+        return _PEER_CACHE[ck]
 
     def _compute_distributed(self, m, n_pos, nan, inf, recall_level):
         import time
@@ -260,82 +279,81 @@ class StreamingEvaluator:
         _raise_nonfinite(gnan, ginf)
         mark("counts_allreduce")
 
-        # 2. global histogram of the top key bits -> splitters
-        keys, labs = be.pairs(self.buf, m)
+        # 2. global histogram of the top key bits (both streams) -> splitters
+        neg, pos = be.streams(self.buf, m, n_pos)
+        n_neg = m - n_pos
         # a systematic sample of ~2^24 keys per rank is plenty to balance the ranges; any splitters give the exact
         # result as long as every rank uses the same ones, which the all_reduce guarantees
         every = max(1, M // (world << SAMPLE_LOG2))
-        hist = be.histogram(keys, m, HIST_BITS, every)
+        hist = be.histogram(neg, n_neg, HIST_BITS, every)
+        if n_pos:
+            hist = hist + be.histogram(pos, n_pos, HIST_BITS, every)
         dist.all_reduce(hist, group=g)
         splitters = choose_splitters(hist.cpu().numpy(), world)
         mark("histogram_splitters")
 
-        # 3. exchange by key range
+        # 3. exchange by key range, stream by stream.  Receive layout on rank r (the evaluator's own layout): negatives
+        #    from source 0, 1, ... upwards from element 0, positives from source 0, 1, ... ending at the capacity.
         exchange = self.exchange
         if exchange == "auto":
-            exchange = "p2p" if hasattr(be, "peer_buffers") and not getattr(self, "_p2p_failed", False) else "nccl"
+            exchange = "p2p" if hasattr(be, "peer_alloc") and not getattr(self, "_p2p_failed", False) else "nccl"
+        send = None
         if exchange == "p2p":
-            # 3a. fused: count -> all-gather of the counts -> ONE kernel that partitions and stores every bucket
-            #     straight into its owner's receive buffer over NVLink (no staging copy, no all-to-all)
-            send_counts = be.partition_count(keys, m, splitters, world)
-            cm = be.tensor(send_counts, torch.int64)
-            all_counts = be.empty(world * world, torch.int64)
-            dist.all_gather_into_tensor(all_counts, cm, group=g)
-            all_counts = all_counts.view(world, world).cpu().numpy()      # [src, dst]
-            recv_counts = [int(c) for c in all_counts[:, rank]]
-            m2 = int(sum(recv_counts))
-            need = int(all_counts.sum(axis=0).max())                      # identical on every rank
-            try:
-                pb = be.peer_buffers(max(need + need // 8, 1 << 20), g)   # collective (re)allocation when it grows
-            except Exception as e:                                        # no peer access on this box: NCCL path
-                self._p2p_failed, self.p2p_error = True, repr(e)
-                pb = None
-            ok = be.tensor([0 if pb is None else 1], torch.int64)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=g)
-            if int(ok.item()) == 1:
-                mark("count")
-                offsets = [int(all_counts[:rank, d].sum()) for d in range(world)]   # my block inside rank d's buffer
-                dist.barrier(group=g)                                     # peers are done with the previous contents
-                be.partition_scatter(keys, labs, m, splitters, world, pb["key_ptrs"], pb["lab_ptrs"], offsets)
-                dist.barrier(group=g)                                     # every rank's stores have landed
-                rk, rl = pb["keys"], pb["labs"]
-                mark("partition_scatter_p2p")
-            else:
+            send = [be.partition_count(neg, n_neg, splitters, world), be.partition_count(pos, n_pos, splitters, world)]
+        else:
+            pk_neg, c_neg = be.partition(neg, n_neg, splitters, world)
+            pk_pos, c_pos = be.partition(pos, n_pos, splitters, world)
+            send = [c_neg, c_pos]
+            mark("partition")
+        cm = be.tensor(send[0] + send[1], torch.int64)
+        all_counts = be.empty(world * 2 * world, torch.int64)
+        dist.all_gather_into_tensor(all_counts, cm, group=g)
+        all_counts = all_counts.view(world, 2, world).cpu().numpy()       # [src, stream, dst]
+        recv_neg = [int(c) for c in all_counts[:, 0, rank]]
+        recv_pos = [int(c) for c in all_counts[:, 1, rank]]
+        m2_neg, m2_pos = int(sum(recv_neg)), int(sum(recv_pos))
+        per_dst = all_counts.sum(axis=0)                                  # [stream, dst]
+        need = int((per_dst[0] + per_dst[1]).max())                       # identical on every rank
+        pb = None
+        if exchange == "p2p":
+            pb = self._peer_buffers(need, g)
+            if pb is None:                                                # agreed on by all ranks: NCCL path
                 self._p2p_failed = True
                 exchange = "nccl"
-        if exchange == "nccl":
-            # 3b. local partition by destination rank + NCCL all-to-all
-            pk, pl, send_counts = be.partition(keys, labs, m, splitters, world)
-            mark("partition")
-            cm = be.tensor(send_counts, torch.int64)
-            all_counts = be.empty(world * world, torch.int64)
-            dist.all_gather_into_tensor(all_counts, cm, group=g)
-            all_counts = all_counts.view(world, world).cpu().numpy()      # [src, dst]
-            recv_counts = [int(c) for c in all_counts[:, rank]]
-            m2 = int(sum(recv_counts))
-            rk, rl = be.empty(max(m2, 1), torch.int32), be.empty(max(m2, 1), torch.uint8)
-            dist.all_to_all_single(rk[:m2], pk, recv_counts, send_counts, group=g)
-            dist.all_to_all_single(rl[:m2], pl, recv_counts, send_counts, group=g)
+                pk_neg, _ = be.partition(neg, n_neg, splitters, world)
+                pk_pos, _ = be.partition(pos, n_pos, splitters, world)
+                mark("partition")
+            else:
+                mark("count")
+        if exchange == "p2p":
+            # 3a. fused: ONE kernel per stream partitions and stores every bucket straight into its owner's receive
+            #     buffer over NVLink (4-byte key stores only; no staging copy, no all-to-all)
+            cap = pb["cap"]
+            off_neg = [int(all_counts[:rank, 0, d].sum()) for d in range(world)]
+            off_pos = [cap - int(per_dst[1][d]) + int(all_counts[:rank, 1, d].sum()) for d in range(world)]
+            dist.barrier(group=g)                                         # peers are done with the previous contents
+            be.partition_scatter(neg, n_neg, splitters, world, pb["key_ptrs"], off_neg)
+            be.partition_scatter(pos, n_pos, splitters, world, pb["key_ptrs"], off_pos)
+            dist.barrier(group=g)                                         # every rank's stores have landed
+            rk = pb["keys"]
+            r_neg, r_pos = rk[:m2_neg], rk[cap - m2_pos: cap]
+            mark("partition_scatter_p2p")
+        else:
+            # 3b. local partition by destination rank + NCCL all-to-all per stream
+            r_neg, r_pos = be.empty(max(m2_neg, 1), torch.int32)[:m2_neg], be.empty(max(m2_pos, 1), torch.int32)[:m2_pos]
+            dist.all_to_all_single(r_neg, pk_neg, recv_neg, send[0], group=g)
+            dist.all_to_all_single(r_pos, pk_pos, recv_pos, send[1], group=g)
             mark("all_to_all")
 
-        # 4. local sort + run-length counts with global prefixes
-        be.sort(rk, rl, m2)
+        # 4. local sort of both streams + merge-path counts with the global prefixes (known from the count matrix)
+        be.sort2(r_neg, m2_neg, r_pos, m2_pos)
         mark("sort")
-        # local cumulative counts first (they also yield this slice's #positives), global prefixes added afterwards:
-        # tps += positives before this rank, fps += negatives before this rank
-        if m2:
-            tps, fps, lp = be.counts_local(rk, rl, m2)
+        neg_before = int(per_dst[0][:rank].sum())
+        pos_before = int(per_dst[1][:rank].sum())
+        if m2_neg + m2_pos:
+            tps, fps = be.counts(r_neg, m2_neg, r_pos, m2_pos, pos_before, neg_before)
         else:
-            tps, fps, lp = be.empty(0, torch.int64), be.empty(0, torch.int64), 0
-        mine = be.tensor([m2, lp], torch.int64)
-        per_rank = be.empty(2 * world, torch.int64)
-        dist.all_gather_into_tensor(per_rank, mine, group=g)
-        per_rank = per_rank.view(world, 2).cpu().numpy()
-        idx_before = int(per_rank[:rank, 0].sum())
-        pos_before = int(per_rank[:rank, 1].sum())
-        if tps.numel():
-            tps += pos_before
-            fps += idx_before - pos_before
+            tps, fps = be.empty(0, torch.int64), be.empty(0, torch.int64)
         mark("counts")
 
         # 5. gather every rank's thresholds (padded to the longest slice), run the identical tail everywhere
@@ -356,7 +374,7 @@ class StreamingEvaluator:
         mark("gather_thresholds")
         res = be.tail(tps_all, fps_all, recall_level)
         mark("tail")
-        self.last_exchange = {"send_counts": send_counts, "recv_counts": recv_counts, "splitters": splitters,
+        self.last_exchange = {"send_counts": send, "recv_counts": [recv_neg, recv_pos], "splitters": splitters,
                               "thresholds_per_rank": Ts, "exchange": exchange,
                               "p2p_error": getattr(self, "p2p_error", None),
                               "phase_ms": {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}}

@@ -31,6 +31,8 @@ def _keep_queries(mask_cls: torch.Tensor, num_classes: int):
 def _run(cls_logits, mask_logits, padded_size, crop_size, want_semseg, want_anomaly, extra_channels, flags=0):
     L.require_cuda(cls_logits, "class logits")
     L.require_cuda(mask_logits, "mask logits")
+    L.forbid_grad("the fused Mask2Former post-head kernel (semantic_inference / get_anomaly_score / post_head_inference)",
+                  cls_logits, mask_logits)
     cls_logits = cls_logits.float().contiguous()
     mask_logits = mask_logits.float().contiguous()
     B, Q, C1 = cls_logits.shape
@@ -82,7 +84,11 @@ def semantic_inference(mask_cls: torch.Tensor, mask_pred: torch.Tensor, num_clas
 
 
 def get_anomaly_score(other_outputs: Dict[str, torch.Tensor], size: Tuple[int, int]) -> torch.Tensor:
-    """train_m2f.py:387-407: ``other_outputs["pred_masks_ood"]`` is the already-upsampled [B, Q, Hp, Wp]."""
+    """train_m2f.py:387-407: ``other_outputs["pred_masks_ood"]`` is the already-upsampled [B, Q, Hp, Wp].
+
+    Forward only (evaluation: test_m2f.py:135, valid_batch): the reference also calls this inside the training loop
+    with autograd on (train_m2f.py:443); there is no backward kernel for the fused Mask2Former path (SURVEY 8f rank 4,
+    Mask2Former half), so inputs that require grad raise ``MssError`` instead of returning a tensor without grad_fn."""
     cls = other_outputs["pred_logits_ood"]
     masks = other_outputs["pred_masks_ood"]
     Hp, Wp = masks.shape[-2:]
@@ -124,6 +130,7 @@ def mask_logits(mask_embed: torch.Tensor, mask_features: torch.Tensor) -> torch.
     ``mask_features`` [B, K, h, w] -> [B, Q, h, w], on tcgen05 with 3xTF32 (fp32-level accuracy)."""
     L.require_cuda(mask_embed, "mask_embed")
     L.require_cuda(mask_features, "mask_features")
+    L.forbid_grad("m2f.mask_logits", mask_embed, mask_features)
     if mask_embed.dim() != 3 or mask_features.dim() != 4:
         raise ValueError("mask_embed must be [B, Q, K] and mask_features [B, K, h, w]")
     e = mask_embed.float().contiguous()

@@ -25,7 +25,7 @@ import torch
 from . import _lib as L
 
 __all__ = ["eval_ood_measure", "get_and_print_results", "get_measures", "fpr_and_fdr_at_recall",
-           "metrics_from_sorted_pairs", "PairBuffer"]
+           "metrics_from_sorted_streams", "PairBuffer"]
 
 
 def _device(*xs) -> torch.device:
@@ -63,17 +63,18 @@ def _as_labels(x, device) -> torch.Tensor:
 
 
 class PairBuffer:
-    """Device buffer of (order-preserving key, 0/1 label) pairs of valid pixels -- the on-device
-    replacement of the testers' ``anomaly_scores`` / ``ood_gts`` host lists
-    (test_deeplab.py:84-101, test_m2f.py:125-144)."""
+    """Device buffer of the order-preserving keys of valid pixels -- the on-device replacement of the testers'
+    ``anomaly_scores`` / ``ood_gts`` host lists (test_deeplab.py:84-101, test_m2f.py:125-144).
+
+    Two key-only streams share ``keys``: in-distribution keys fill ``keys[0:n_neg]`` upwards, OOD keys fill
+    ``keys[capacity - n_pos:]`` downwards; the 0/1 label of a pixel is the stream its key is in (no label bytes)."""
 
     def __init__(self, capacity: int, device):
         self.device = torch.device(device)
         self.capacity = int(capacity)
         self.keys = torch.empty(max(self.capacity, 1), dtype=torch.int32, device=self.device)
-        self.labs = torch.empty(max(self.capacity, 1), dtype=torch.uint8, device=self.device)
         self.state = torch.zeros(L.EVAL_STATE_BYTES, dtype=torch.uint8, device=self.device)
-        self.c = L.EvalBuffers(self.keys.data_ptr(), self.labs.data_ptr(), self.state.data_ptr(), self.capacity)
+        self.c = L.EvalBuffers(self.keys.data_ptr(), self.state.data_ptr(), self.capacity)
 
     def reset(self):
         with torch.cuda.device(self.device):
@@ -86,17 +87,21 @@ class PairBuffer:
                                              scores.numel(), id_in, id_out, C.byref(self.c),
                                              L.stream_ptr(self.device)), "mss_eval_append")
 
+    def streams(self, count: int, n_pos: int):
+        """-> (negative keys, positive keys) views for a state (count, n_pos) read with ``read_state``."""
+        return self.keys[: count - n_pos], self.keys[self.capacity - n_pos: self.capacity]
+
     def grow(self, capacity: int):
-        """Enlarge (keeps the appended pairs)."""
+        """Enlarge (keeps the appended keys)."""
         if capacity <= self.capacity:
             return
-        m = self.read_state()[0]
+        m, n_pos, _, _ = self.read_state()
         keys = torch.empty(capacity, dtype=torch.int32, device=self.device)
-        labs = torch.empty(capacity, dtype=torch.uint8, device=self.device)
-        keys[:m].copy_(self.keys[:m])
-        labs[:m].copy_(self.labs[:m])
-        self.keys, self.labs, self.capacity = keys, labs, int(capacity)
-        self.c = L.EvalBuffers(self.keys.data_ptr(), self.labs.data_ptr(), self.state.data_ptr(), self.capacity)
+        neg, pos = self.streams(m, n_pos)
+        keys[: m - n_pos].copy_(neg)
+        keys[capacity - n_pos:].copy_(pos)
+        self.keys, self.capacity = keys, int(capacity)
+        self.c = L.EvalBuffers(self.keys.data_ptr(), self.state.data_ptr(), self.capacity)
 
     def read_state(self) -> Tuple[int, int, int, int]:
         """(count, n_pos, nan_flag, inf_flag); synchronises the stream."""
@@ -106,33 +111,44 @@ class PairBuffer:
                     "mss_eval_state_host")
         return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
+    def sort(self, n_upper: int):
+        """Sort both streams in place (one sequence of launches; stream sizes are read from the device state)."""
+        lib = L.load()
+        with torch.cuda.device(self.device):
+            nbytes = lib.mss_sort_keys_workspace_bytes(n_upper)
+            ws = L.workspace(nbytes, self.device)
+            L.check(lib.mss_eval_sort(C.byref(self.c), n_upper, ws.data_ptr(), nbytes, L.stream_ptr(self.device)),
+                    "mss_eval_sort")
+        del ws
 
-def sort_pairs(keys: torch.Tensor, labs: torch.Tensor, m: int):
-    dev = keys.device
+
+def sort_keys(keys_a: torch.Tensor, n_a: int, keys_b: Optional[torch.Tensor] = None, n_b: int = 0):
+    """Ascending in-place sort of one or two independent uint32 key arrays (int32 tensors holding the bits)."""
+    dev = keys_a.device
     lib = L.load()
     with torch.cuda.device(dev):
-        nbytes = lib.mss_sort_pairs_workspace_bytes(m)
+        nbytes = lib.mss_sort_keys_workspace_bytes(n_a + n_b)
         ws = L.workspace(nbytes, dev)
-        L.check(lib.mss_sort_pairs(keys.data_ptr(), labs.data_ptr(), m, ws.data_ptr(), nbytes, L.stream_ptr(dev)),
-                "mss_sort_pairs")
+        L.check(lib.mss_sort_keys(keys_a.data_ptr(), n_a, L.ptr(keys_b), n_b, ws.data_ptr(), nbytes, L.stream_ptr(dev)),
+                "mss_sort_keys")
     del ws
 
 
-def counts_from_sorted(keys, labs, m: int, pos_before: int = 0, idx_before: int = 0):
-    """-> (tps[T], fps[T] int64 device tensors, n_pos, n_neg)."""
-    dev = keys.device
+def counts_from_sorted(neg_keys, n_neg: int, pos_keys, n_pos: int, pos_before: int = 0, neg_before: int = 0):
+    """Two sorted key streams -> (tps[T], fps[T]) int64 device tensors (cumulative counts per distinct key)."""
+    dev = neg_keys.device if neg_keys is not None else pos_keys.device
     lib = L.load()
+    n = n_neg + n_pos
     with torch.cuda.device(dev):
-        tps = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
-        fps = torch.empty(max(m, 1), dtype=torch.int64, device=dev)
-        nbytes = lib.mss_counts_workspace_bytes(m)
+        tps = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        fps = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+        nbytes = lib.mss_counts_workspace_bytes(n)
         ws = L.workspace(nbytes, dev)
         T = C.c_int64(0)
-        pn = (C.c_int64 * 2)()
-        L.check(lib.mss_counts_from_sorted(keys.data_ptr(), labs.data_ptr(), m, pos_before, idx_before,
-                                           tps.data_ptr(), fps.data_ptr(), C.byref(T), pn, ws.data_ptr(), nbytes,
+        L.check(lib.mss_counts_from_sorted(L.ptr(neg_keys), n_neg, L.ptr(pos_keys), n_pos, pos_before, neg_before,
+                                           tps.data_ptr(), fps.data_ptr(), C.byref(T), ws.data_ptr(), nbytes,
                                            L.stream_ptr(dev)), "mss_counts_from_sorted")
-    return tps[:T.value], fps[:T.value], int(pn[0]), int(pn[1])
+    return tps[:T.value], fps[:T.value]
 
 
 def metrics_tail(tps: torch.Tensor, fps: torch.Tensor, recall_level: float = 0.95):
@@ -155,10 +171,15 @@ def metrics_tail(tps: torch.Tensor, fps: torch.Tensor, recall_level: float = 0.9
     return (np.float64(out[0]), np.float64(out[1]), np.float64(out[2])), int(t_roc.value)
 
 
-def metrics_from_sorted_pairs(keys, labs, m: int, recall_level: float = 0.95):
-    tps, fps, _, _ = counts_from_sorted(keys, labs, m)
+def metrics_from_sorted_streams(neg_keys, n_neg: int, pos_keys, n_pos: int, recall_level: float = 0.95):
+    tps, fps = counts_from_sorted(neg_keys, n_neg, pos_keys, n_pos)
     res, _ = metrics_tail(tps, fps, recall_level)
     return res
+
+
+# up to this many keys the C composite runs (every stage sized for the upper bound, two host round trips in all);
+# beyond it the stages run one by one so that the float64 tail is sized by the actual number of thresholds
+_FUSED_MAX = 1 << 28
 
 
 def _finish(buf: PairBuffer, recall_level: float = 0.95, check_empty: bool = True):
@@ -169,8 +190,20 @@ def _finish(buf: PairBuffer, recall_level: float = 0.95, check_empty: bool = Tru
         raise ValueError("Input contains NaN.")                   # sklearn assert_all_finite
     if inf:
         raise ValueError("Input contains infinity or a value too large for dtype('float32').")
-    sort_pairs(buf.keys, buf.labs, m)
-    return metrics_from_sorted_pairs(buf.keys, buf.labs, m, recall_level)
+    if m <= _FUSED_MAX and recall_level == 0.95:
+        lib = L.load()
+        with torch.cuda.device(buf.device):
+            nbytes = lib.mss_ood_metrics_from_eval_workspace_bytes(m)
+            ws = L.workspace(nbytes, buf.device)
+            out = (C.c_double * 3)()
+            rc = L.check(lib.mss_ood_metrics_from_eval(C.byref(buf.c), ws.data_ptr(), nbytes, out, None,
+                                                       L.stream_ptr(buf.device)), "mss_ood_metrics_from_eval")
+        if rc == L.MSS_EMPTY_CLASS:
+            return None
+        return np.float64(out[0]), np.float64(out[1]), np.float64(out[2])
+    buf.sort(m)
+    neg, pos = buf.streams(m, n_pos)
+    return metrics_from_sorted_streams(neg, m - n_pos, pos, n_pos, recall_level)
 
 
 def eval_ood_measure(conf, seg_label, train_id_in=0, train_id_out=1) -> Optional[Tuple[float, float, float]]:
@@ -181,11 +214,26 @@ def eval_ood_measure(conf, seg_label, train_id_in=0, train_id_out=1) -> Optional
     labels = _as_labels(seg_label, dev)
     if scores.numel() != labels.numel():
         raise IndexError("conf and seg_label differ in size")     # numpy boolean-index error in the reference
-    if scores.numel() == 0:
+    n = scores.numel()
+    if n == 0:
         return None
-    buf = PairBuffer(scores.numel(), dev)
-    buf.append(scores, labels, int(train_id_in), int(train_id_out))
-    return _finish(buf)
+    if n > _FUSED_MAX:
+        buf = PairBuffer(n, dev)
+        buf.reset()
+        buf.append(scores, labels, int(train_id_in), int(train_id_out))
+        return _finish(buf)
+    # one C call: selection + key build + sort + counts + ROC compaction enqueued back to back, two host syncs in all
+    lib = L.load()
+    with torch.cuda.device(dev):
+        nbytes = lib.mss_ood_metrics_workspace_bytes(n)
+        ws = L.workspace(nbytes, dev)
+        out = (C.c_double * 3)()
+        rc = L.check(lib.mss_ood_metrics(scores.data_ptr(), labels.data_ptr(), L.label_code(labels), n, int(train_id_in),
+                                         int(train_id_out), ws.data_ptr(), nbytes, out, None, L.stream_ptr(dev)),
+                     "mss_ood_metrics")
+    if rc == L.MSS_EMPTY_CLASS:
+        return None
+    return np.float64(out[0]), np.float64(out[1]), np.float64(out[2])
 
 
 def get_measures(_pos, _neg, recall_level=0.95):

@@ -7,8 +7,9 @@
 
 The per-pixel work -- the confusion histogram over the whole dataset -- runs on the GPU (integer,
 bit-exact; ``mss_confusion_hist`` / ``mss_confusion_from_logits``).  What is left for the host is the
-closed-form arithmetic on the 19 x 19 matrix, done with the very numpy expressions the reference uses so
-the float64 results are identical.  ``ConfusionAccumulator`` is the streaming form: it keeps
+closed-form arithmetic on the 19 x 19 matrix; it sits behind the C ABI as well (``mss_confusion_scores``, host-only,
+IEEE float64 operation by operation in numpy's order -- pinned to reference-generated fixtures by the CPU test-suite),
+so C callers get the same numbers.  ``ConfusionAccumulator`` is the streaming form: it keeps
 ``hist/labeled/correct`` on the device across batches (``compute_metric``'s accumulation loop) and can take
 the NCHW logits directly (argmax fused, the int64 prediction map is never written).
 """
@@ -87,10 +88,16 @@ class ConfusionAccumulator:
                                                        L.stream_ptr(self.device)), "mss_confusion_from_logits")
 
     def result(self):
-        """-> (hist [n_cl, n_cl] int64 ndarray, labeled, correct) -- one small D2H."""
-        h = self.hist.cpu().numpy().reshape(self.n_cl, self.n_cl)
-        lc = self.lc.cpu().numpy()
-        return h, np.int64(lc[0]), np.int64(lc[1])
+        """-> (hist [n_cl, n_cl] int64 ndarray, labeled, correct) -- the one synchronisation of a streaming evaluation.
+        Raises ``ValueError`` if any update saw a labeled pixel whose ``n_cl * gt + pred`` is out of range (numpy's
+        bincount / reshape raise in the reference, metric.py:15-17)."""
+        import ctypes as C
+        h = np.empty(self.n_cl * self.n_cl, dtype=np.int64)
+        lc = (C.c_int64 * 2)()
+        with torch.cuda.device(self.device):
+            L.check(L.load().mss_confusion_result(self.hist.data_ptr(), self.lc.data_ptr(), self.n_cl, h.ctypes.data, lc,
+                                                  L.stream_ptr(self.device)), "mss_confusion_result")
+        return h.reshape(self.n_cl, self.n_cl), np.int64(lc[0]), np.int64(lc[1])
 
     def compute(self, per_class: bool = False):
         h, labeled, correct = self.result()
@@ -104,24 +111,34 @@ def hist_info(n_cl, pred, gt):
     return acc.result()
 
 
+def _scores(hist, correct, labeled, per_class: bool):
+    """metric.py:42-64 through the C ABI (``mss_confusion_scores``; host-only, no device work)."""
+    import ctypes as C
+    import warnings
+    h = np.ascontiguousarray(hist, dtype=np.float64)
+    n_cl = h.shape[0]
+    if h.shape != (n_cl, n_cl):
+        raise ValueError("hist must be a square [n_cl, n_cl] matrix")
+    iu = np.empty(n_cl, dtype=np.float64)
+    acc = np.empty(n_cl, dtype=np.float64)
+    out = (C.c_double * 3)()
+    L.check(L.load().mss_confusion_scores(h.ctypes.data, n_cl, float(correct), float(labeled), 1 if per_class else 0,
+                                          iu.ctypes.data, acc.ctypes.data, out), "mss_confusion_scores")
+    if np.isnan(iu).any() or float(labeled) == 0.0:          # the reference's numpy expressions warn here (0 / 0)
+        warnings.warn("invalid value encountered in divide", RuntimeWarning, stacklevel=3)
+    return iu, acc, np.float64(out[0]), np.float64(out[1]), np.float64(out[2])
+
+
 def compute_score(hist, correct, labeled):
-    """metric.py:42-49 (same numpy expressions; 0/0 classes give nan + a RuntimeWarning as in the reference)."""
-    iu = np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
-    mean_IU = np.nanmean(iu)
-    mean_IU_no_back = np.nanmean(iu[1:])
-    mean_pixel_acc = correct / labeled
-    return iu, mean_IU, mean_IU_no_back, mean_pixel_acc
+    """metric.py:42-49 -> (iu, mean_IU, mean_IU_no_back, mean_pixel_acc); classes absent from both maps give nan."""
+    iu, _, mean_iu, mean_iu_nb, pix = _scores(hist, correct, labeled, False)
+    return iu, mean_iu, mean_iu_nb, pix
 
 
 def compute_score_per_class(hist, correct, labeled):
-    """metric.py:51-64."""
-    intersection = np.diag(hist)
-    union = hist.sum(axis=1) + hist.sum(axis=0) - np.diag(hist)
-    iu = intersection / np.maximum(union, 1)
-    class_acc = intersection / np.maximum(hist.sum(axis=1), 1)
-    mean_IU = np.nanmean(iu)
-    mean_pixel_acc = correct / labeled
-    return iu, mean_IU, class_acc, mean_pixel_acc
+    """metric.py:51-64 -> (iu, mean_IU, class_acc, mean_pixel_acc)."""
+    iu, acc, mean_iu, _, pix = _scores(hist, correct, labeled, True)
+    return iu, mean_iu, acc, pix
 
 
 def compute_metric(results, per_class=False):

@@ -24,7 +24,7 @@ def lib_path():
 def test_header_declares_entry_points():
     syms = declared_symbols()
     for must in ["mss_deeplab_score", "mss_upsample_bilinear", "mss_m2f_semantic_inference", "mss_ood_metrics",
-                 "mss_sort_pairs", "mss_metrics_tail", "mss_eval_append", "mss_last_error"]:
+                 "mss_sort_keys", "mss_eval_sort", "mss_counts_from_sorted", "mss_partition_scatter_keys", "mss_metrics_tail", "mss_eval_append", "mss_last_error"]:
         assert must in syms
 
 
@@ -38,9 +38,9 @@ def test_ctypes_table_matches_header(lib_path):
     from multishiftseg_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.mss_abi_version() == 1
+    assert lib.mss_abi_version() == 2
     # pure host-side size queries are callable without a GPU
-    assert lib.mss_sort_pairs_workspace_bytes(1 << 20) > (1 << 20) * 5
+    assert lib.mss_sort_keys_workspace_bytes(1 << 20) > (1 << 20) * 4
     assert lib.mss_ood_metrics_workspace_bytes(1000) > 0
     assert lib.mss_tail_workspace_bytes(10) > 0
     assert lib.mss_m2f_workspace_bytes(2, 100, 19) >= 2 * 100 * 20 * 4
@@ -131,3 +131,16 @@ def test_pairwise_plan_and_combine_equal_numpy_sum(lib_path, n):
     out = C.c_double()
     assert L.load().mss_pairwise_sum_host(a.ctypes.data, n, C.byref(out)) == 0, L.last_error()
     assert out.value == float(np.sum(a))
+
+
+def test_forward_only_entry_points_refuse_autograd_inputs():
+    """m2f.* / head_scores / score_maps have no backward; with grad-tracked inputs they must raise instead of
+    silently returning tensors without grad_fn (host-side check, runs before any device work)."""
+    import torch
+    from multishiftseg_b200 import _lib
+    x = torch.zeros(3, requires_grad=True)
+    with pytest.raises(_lib.MssError):
+        _lib.forbid_grad("op", x)
+    with torch.no_grad():
+        _lib.forbid_grad("op", x)                      # inference: fine
+    _lib.forbid_grad("op", x.detach(), None, 3)

@@ -112,24 +112,68 @@ def test_get_measures_and_fpr(M):
 
 
 # ------------------------------------------------------------------------------------ integer stages
-def test_sort_pairs_exact(M):
+def _keys_t(k):
+    return torch.from_numpy(np.ascontiguousarray(k).view(np.int32)).cuda()
+
+
+def _keys_np(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def test_sort_keys_exact(M):
     rng = np.random.default_rng(0)
     for n in [1, 2, 31, 4096, 4097, 100_000, 3_000_001]:
         k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
         if n > 1000:
             k[: n // 3] &= np.uint32(0xFF)              # heavy ties / skewed high digits
-        v = rng.integers(0, 2, size=n, dtype=np.uint8)
-        kt = torch.from_numpy(k.view(np.int32)).cuda()
-        vt = torch.from_numpy(v).cuda()
-        M.sort_pairs(kt, vt, n)
-        order = np.argsort(k, kind="stable")
-        assert np.array_equal(kt.cpu().numpy().view(np.uint32), k[order])
-        assert np.array_equal(vt.cpu().numpy(), v[order])       # stable: payload follows input order inside ties
+        kt = _keys_t(k)
+        M.sort_keys(kt, n)
+        assert np.array_equal(_keys_np(kt), np.sort(k))
 
 
-def test_sort_pairs_histogram_counter_fold():
+@pytest.mark.parametrize("na,nb", [(0, 5), (5, 0), (1, 1), (4096, 4096), (4097, 1), (100_003, 7_001), (2_000_001, 300_007),
+                                   (7, 1_000_003)])
+def test_sort_two_segments_one_launch_sequence(M, na, nb):
+    """Both streams of an evaluation are sorted by one sequence of launches (tiles numbered over both segments,
+    look-back confined to the segment); unaligned second segment."""
+    rng = np.random.default_rng(na * 31 + nb)
+    a = rng.integers(0, 2 ** 32, size=na, dtype=np.uint64).astype(np.uint32)
+    b = (rng.integers(0, 2 ** 32, size=nb, dtype=np.uint64).astype(np.uint32) >> np.uint32(9)) | np.uint32(0x3F000000)
+    buf = torch.full((na + nb + 7,), -1, dtype=torch.int32, device="cuda")
+    ta, tb = buf[:na], buf[na + 3: na + 3 + nb]         # the second array starts 4-byte aligned only
+    ta.copy_(_keys_t(a)); tb.copy_(_keys_t(b))
+    M.sort_keys(ta, na, tb, nb)
+    assert np.array_equal(_keys_np(ta), np.sort(a)) and np.array_equal(_keys_np(tb), np.sort(b))
+    assert (buf[na: na + 3] == -1).all() and (buf[na + 3 + nb:] == -1).all()      # nothing outside the arrays
+
+
+@pytest.mark.parametrize("mode", ["low_byte_constant", "fp16_born", "all_equal", "top_byte_constant"])
+def test_sort_single_bin_pass_skip(M, mode):
+    """A digit that is the same for every key of a segment is skipped on the device (odd number of live passes:
+    the result is copied back); compared with the un-skipped sort in a subprocess (MSS_SORT_NOSKIP=1)."""
+    rng = np.random.default_rng(5)
+    n = 1_000_003
+    k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    if mode == "low_byte_constant":
+        k = (k & np.uint32(0xFFFFFF00)) | np.uint32(0x5A)
+    elif mode == "fp16_born":
+        s = rng.standard_normal(n).astype(np.float16).astype(np.float32)
+        k = mo.float_key_desc(s)
+    elif mode == "all_equal":
+        k[:] = 0xDEADBEEF
+    else:
+        k = (k & np.uint32(0x00FFFFFF)) | np.uint32(0x42000000)
+    kt = _keys_t(k)
+    other = _keys_t(k[::-1].copy()[: n // 3])           # second segment with its own skip decisions
+    M.sort_keys(kt, n, other, n // 3)
+    assert np.array_equal(_keys_np(kt), np.sort(k))
+    assert np.array_equal(_keys_np(other), np.sort(k[::-1][: n // 3]))
+
+
+def test_sort_histogram_counter_fold():
     """The upfront digit histogram keeps 16-bit lane-private counters and folds them every HIST_EPOCH chunks;
-    MSS_HIST_EPOCH=2 (read once per process) makes a 5 M-key input cross many folds.  Unaligned key pointer too."""
+    MSS_HIST_EPOCH=2 (read once per process) makes a 5 M-key input cross many folds.  Unaligned key pointer too.
+    MSS_SORT_NOSKIP=1: the same process also checks the sort with the pass skip disabled."""
     import subprocess
     import sys
     code = r"""
@@ -141,37 +185,51 @@ n = 5_000_003
 k = rng.integers(0, 2 ** 32, size=n + 1, dtype=np.uint64).astype(np.uint32)
 k[: n // 2] &= np.uint32(0x0000FFFF)
 k[n // 2: n // 2 + n // 4] |= np.uint32(0xFFFF0000)
-v = rng.integers(0, 2, size=n + 1, dtype=np.uint8)
 kt = torch.from_numpy(k.view(np.int32)).cuda()[1:]          # 4-byte aligned, not 16
-vt = torch.from_numpy(v).cuda()[1:].clone()
-M.sort_pairs(kt, vt, n)
-order = np.argsort(k[1:], kind="stable")
-assert np.array_equal(kt.cpu().numpy().view(np.uint32), k[1:][order])
-assert np.array_equal(vt.cpu().numpy(), v[1:][order])
+M.sort_keys(kt, n)
+assert np.array_equal(kt.cpu().numpy().view(np.uint32), np.sort(k[1:]))
+k2 = (k[1:] & np.uint32(0xFFFFFF00)).copy()                  # low byte constant, skip disabled by the env
+kt2 = torch.from_numpy(k2.view(np.int32)).cuda()
+M.sort_keys(kt2, n)
+assert np.array_equal(kt2.cpu().numpy().view(np.uint32), np.sort(k2))
 print("fold ok")
 """
-    env = dict(os.environ, MSS_HIST_EPOCH="2")
+    env = dict(os.environ, MSS_HIST_EPOCH="2", MSS_SORT_NOSKIP="1")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "fold ok" in r.stdout, r.stdout + r.stderr
 
 
-def test_counts_and_tail_stage_level(M):
-    s, l = gi.metric_case(11, 300_000, "f16", label_dtype="uint8")
-    tps_ref, fps_ref = mo.ood_counts(s, l)
-    valid = l != 255
-    key = mo.float_key_desc(s[valid])
-    order = np.argsort(key, kind="stable")
-    kt = torch.from_numpy(key[order].view(np.int32)).cuda()
-    vt = torch.from_numpy((l[valid] == 1).astype(np.uint8)[order]).cuda()
-    tps, fps, npos, nneg = M.counts_from_sorted(kt, vt, kt.numel())
+def _streams(s, l):
+    """oracle-side streams: sorted negative / positive keys of the valid pixels"""
+    return np.sort(mo.float_key_desc(s[l == 0])), np.sort(mo.float_key_desc(s[l == 1]))
+
+
+@pytest.mark.parametrize("n,mode,p_ood", [(300_000, "f16", 0.05), (1_000_003, "cont", 0.5), (50_000, "const", 0.3),
+                                          (2049, "q2", 0.1), (2048, "cont", 0.0), (2047, "cont", 1.0), (5_000_011, "q2", 0.02)])
+def test_counts_and_tail_stage_level(M, n, mode, p_ood):
+    """merge-path counts over the two sorted streams == the integer spec (oracle.ood_counts), with and without the
+    multi-GPU prefixes; the tail over them == the C oracle."""
+    s, l = gi.metric_case(11, n, mode, p_ood, 0.05, label_dtype="uint8")
+    if p_ood == 0.0:
+        l[l == 1] = 0
+    if p_ood == 1.0:
+        l[l == 0] = 1
+    neg, pos = _streams(s, l)
+    nt, pt = _keys_t(neg), _keys_t(pos)
+    tps, fps = M.counts_from_sorted(nt, neg.size, pt, pos.size)
+    keys = np.unique(np.concatenate([neg, pos]))
+    tps_ref = np.searchsorted(pos, keys, side="right")
+    fps_ref = np.searchsorted(neg, keys, side="right")
     assert np.array_equal(tps.cpu().numpy(), tps_ref) and np.array_equal(fps.cpu().numpy(), fps_ref)
-    assert (npos, nneg) == (int(tps_ref[-1]), int(fps_ref[-1]))
-    # offsets (the multi-GPU path): global prefixes are added exactly
-    tps2, fps2, _, _ = M.counts_from_sorted(kt, vt, kt.numel(), pos_before=10, idx_before=100)
-    assert np.array_equal(tps2.cpu().numpy(), tps_ref + 10) and np.array_equal(fps2.cpu().numpy(), fps_ref + 90)
-    res, t_roc = M.metrics_tail(tps, fps)
-    assert _tup(res) == c_oracle.metrics_from_counts(tps_ref, fps_ref)
+    if 0.0 < p_ood < 1.0:
+        t2, f2 = mo.ood_counts(s, l)
+        assert np.array_equal(tps_ref, t2) and np.array_equal(fps_ref, f2)
+        # offsets (the multi-GPU path): global prefixes are added exactly
+        tps2, fps2 = M.counts_from_sorted(nt, neg.size, pt, pos.size, pos_before=10, neg_before=90)
+        assert np.array_equal(tps2.cpu().numpy(), tps_ref + 10) and np.array_equal(fps2.cpu().numpy(), fps_ref + 90)
+        res, t_roc = M.metrics_tail(tps, fps)
+        assert _tup(res) == c_oracle.metrics_from_counts(tps_ref, fps_ref)
 
 
 def test_histogram_and_partition(M):
@@ -180,26 +238,22 @@ def test_histogram_and_partition(M):
     rng = np.random.default_rng(3)
     n = 1_234_567
     k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
-    v = rng.integers(0, 2, size=n, dtype=np.uint8)
-    kt = torch.from_numpy(k.view(np.int32)).cuda()
-    vt = torch.from_numpy(v).cuda()
+    kt = _keys_t(k)
     st = torch.cuda.current_stream().cuda_stream
     hist = torch.empty(1 << 16, dtype=torch.int64, device="cuda")
     assert lib.mss_keys_histogram(kt.data_ptr(), n, 16, hist.data_ptr(), st) == 0
     assert np.array_equal(hist.cpu().numpy(), np.bincount(k >> 16, minlength=1 << 16))
     spl = np.array([1 << 30, 1 << 31, 3 << 30], dtype=np.uint32)
-    splt = torch.from_numpy(spl.view(np.int32)).cuda()
-    ko, vo = torch.empty_like(kt), torch.empty_like(vt)
-    nb = lib.mss_partition_workspace_bytes(n)
+    splt = _keys_t(spl)
+    ko = torch.empty_like(kt)
+    nb = lib.mss_partition_workspace_bytes(n, 4)
     ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
     counts = (C.c_int64 * 4)()
-    assert lib.mss_partition_pairs(kt.data_ptr(), vt.data_ptr(), n, splt.data_ptr(), 4, ko.data_ptr(), vo.data_ptr(),
-                                   counts, ws.data_ptr(), nb, st) == 0
+    assert lib.mss_partition_keys(kt.data_ptr(), n, splt.data_ptr(), 4, ko.data_ptr(), counts, ws.data_ptr(), nb, st) == 0, L.last_error()
     dest = np.searchsorted(spl, k, side="right")
     order = np.argsort(dest, kind="stable")
     assert list(counts) == np.bincount(dest, minlength=4).tolist()
-    assert np.array_equal(ko.cpu().numpy().view(np.uint32), k[order])
-    assert np.array_equal(vo.cpu().numpy(), v[order])
+    assert np.array_equal(_keys_np(ko), k[order])
 
 
 @pytest.mark.parametrize("bits", [16, 15, 12, 3])
@@ -236,7 +290,7 @@ def test_keys_histogram_sampled(M):
         assert np.array_equal(hist.cpu().numpy(), np.bincount(sample >> 16, minlength=1 << 16))
 
 
-@pytest.mark.parametrize("parts", [1, 2, 8, 16, 17, 200])
+@pytest.mark.parametrize("parts", [1, 2, 3, 8, 16, 17, 200, 256])
 def test_partition_many_and_few_parts(M, parts):
     from multishiftseg_b200 import _lib as L
     lib = L.load()
@@ -244,49 +298,58 @@ def test_partition_many_and_few_parts(M, parts):
     n = 777_777
     k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
     k[: n // 2] = (k[: n // 2] >> 12) | np.uint32(0x40000000)               # half the keys in a narrow range
-    v = rng.integers(0, 2, size=n, dtype=np.uint8)
+    k[:5] = 0xFFFFFFFF                                                      # the largest key (beyond every splitter)
     spl = np.sort(rng.choice(k, size=parts - 1, replace=False)).astype(np.uint32) if parts > 1 else np.zeros(0, np.uint32)
-    kt, vt = torch.from_numpy(k.view(np.int32)).cuda(), torch.from_numpy(v).cuda()
-    splt = torch.from_numpy(np.concatenate([spl, np.zeros(1, np.uint32)]).view(np.int32)).cuda()
-    ko, vo = torch.empty_like(kt), torch.empty_like(vt)
-    nb = lib.mss_partition_workspace_bytes(n)
+    kt = _keys_t(k)
+    splt = _keys_t(np.concatenate([spl, np.zeros(1, np.uint32)]))
+    ko = torch.empty_like(kt)
+    nb = lib.mss_partition_workspace_bytes(n, parts)
     ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
     counts = (C.c_int64 * parts)()
     st = torch.cuda.current_stream().cuda_stream
-    assert lib.mss_partition_pairs(kt.data_ptr(), vt.data_ptr(), n, splt.data_ptr(), parts, ko.data_ptr(), vo.data_ptr(),
-                                   counts, ws.data_ptr(), nb, st) == 0
+    assert lib.mss_partition_keys(kt.data_ptr(), n, splt.data_ptr(), parts, ko.data_ptr(), counts, ws.data_ptr(), nb, st) == 0, L.last_error()
     dest = np.searchsorted(spl, k, side="right")
     order = np.argsort(dest, kind="stable")
     assert list(counts) == np.bincount(dest, minlength=parts).tolist()
-    assert np.array_equal(ko.cpu().numpy().view(np.uint32), k[order])
-    assert np.array_equal(vo.cpu().numpy(), v[order])
+    assert np.array_equal(_keys_np(ko), k[order])
 
 
 @pytest.mark.parametrize("parts", [2, 8])
 def test_partition_scatter_to_separate_buffers(M, parts):
-    """mss_partition_count + mss_partition_scatter_pairs with one buffer pair per bucket (on a multi-GPU box these
+    """mss_partition_count + mss_partition_scatter_keys with one buffer per bucket (on a multi-GPU box these
     are the peers' receive buffers; here they are local): == the stable partition, bucket by bucket."""
     from multishiftseg_b200.evaluator import CudaBackend
     be = CudaBackend("cuda")
     rng = np.random.default_rng(parts)
     n = 1_000_001
     k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
-    v = rng.integers(0, 2, size=n, dtype=np.uint8)
     spl = [int(x) for x in np.sort(rng.choice(k, size=parts - 1, replace=False))]
-    kt, vt = torch.from_numpy(k.view(np.int32)).cuda(), torch.from_numpy(v).cuda()
+    kt = _keys_t(k)
     counts = be.partition_count(kt, n, spl, parts)
     dest = np.searchsorted(np.asarray(spl, dtype=np.uint32), k, side="right")
     assert counts == np.bincount(dest, minlength=parts).tolist()
     off = 5                                                           # this "rank's" block starts at element 5
     bk = [torch.full((c + off + 3,), -1, dtype=torch.int32, device="cuda") for c in counts]
-    bl = [torch.full((c + off + 3,), 9, dtype=torch.uint8, device="cuda") for c in counts]
-    be.partition_scatter(kt, vt, n, spl, parts, [t.data_ptr() for t in bk], [t.data_ptr() for t in bl], [off] * parts)
+    be.partition_scatter(kt, n, spl, parts, [t.data_ptr() for t in bk], [off] * parts)
     for d in range(parts):
         sel = dest == d
-        assert np.array_equal(bk[d].cpu().numpy().view(np.uint32)[off:off + counts[d]], k[sel])      # stable
-        assert np.array_equal(bl[d].cpu().numpy()[off:off + counts[d]], v[sel])
+        assert np.array_equal(_keys_np(bk[d])[off:off + counts[d]], k[sel])      # stable
         assert (bk[d][:off] == -1).all() and (bk[d][off + counts[d]:] == -1).all()                    # nothing outside the block
-        assert (bl[d][:off] == 9).all() and (bl[d][off + counts[d]:] == 9).all()
+
+
+def test_two_stream_buffer_layout_and_grow(M):
+    """in-distribution keys grow upwards from 0, OOD keys downwards from the capacity; grow() keeps both."""
+    s, l = gi.metric_case(21, 100_000, "cont", 0.1, 0.1, label_dtype="uint8")
+    buf = M.PairBuffer(s.size, "cuda")
+    buf.append(torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda())
+    m, n_pos, nan, inf = buf.read_state()
+    assert (m, n_pos, nan, inf) == (int((l != 255).sum()), int((l == 1).sum()), 0, 0)
+    neg, pos = buf.streams(m, n_pos)
+    assert np.array_equal(np.sort(_keys_np(neg)), np.sort(mo.float_key_desc(s[l == 0])))
+    assert np.array_equal(np.sort(_keys_np(pos)), np.sort(mo.float_key_desc(s[l == 1])))
+    buf.grow(3 * s.size)
+    buf.append(torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda())
+    assert _tup(M._finish(buf)) == c_oracle.eval_ood_measure(np.concatenate([s, s]), np.concatenate([l, l]))
 
 
 def test_one_shot_c_entry(M):
