@@ -224,6 +224,11 @@ MSS_API int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int64_
  * so the multi-GPU evaluator histograms ~2^24 keys per rank instead of all of them. */
 MSS_API int mss_keys_histogram_sampled(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist,
                                void *stream);
+/* second level of the same (same sampling): hist[65536] of the LOW 16 bits of the keys whose top 16 bits equal prefix16.
+ * Lets a splitter fall INSIDE a heavy top-16-bit bin (saturated or narrow-range scores), so that one rank does not
+ * end up owning the whole dataset. */
+MSS_API int mss_keys_histogram_refine(const uint32_t *keys, int64_t n, unsigned prefix16, int every, int64_t *hist,
+                              void *stream);
 /* stable partition of keys into `parts` (<= 256) destination ranges:
  * dest(key) = #{ j : key >= splitters[j] }, splitters ascending device array [parts-1].
  * out_counts_host[parts] receives the bucket sizes (synchronises the stream). */

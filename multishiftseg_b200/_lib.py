@@ -74,6 +74,7 @@ SIGNATURES = {
     "mss_eval_sort": (_i, [_EV, _i64, _p, _sz, _p]),
     "mss_keys_histogram": (_i, [_p, _i64, _i, _p, _p]),
     "mss_keys_histogram_sampled": (_i, [_p, _i64, _i, _i, _p, _p]),
+    "mss_keys_histogram_refine": (_i, [_p, _i64, _u, _i, _p, _p]),
     "mss_partition_workspace_bytes": (_sz, [_i64, _i]),
     "mss_partition_keys": (_i, [_p, _i64, _p, _i, _p, _p, _p, _sz, _p]),
     "mss_partition_count": (_i, [_p, _i64, _p, _i, _p, _p, _sz, _p]),

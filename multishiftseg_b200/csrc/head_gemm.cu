@@ -132,7 +132,7 @@ extern "C" int mss_deeplab_head(const float *feature, int64_t B, int K, int64_t 
     head_weights_umma_kernel<<<(K * HG_N + 255) / 256, 256, 0, st>>>(w_cls, w_ood, C, K, table);
     MSS_CHECK_LAUNCH();
     const int tiles_per_image = (int)((hw + 127) / 128);
-    const PixelGemmPlan plan = pixel_gemm_plan(B, tiles_per_image, sm_count());
+    const PixelGemmPlan plan = pixel_gemm_plan(B, tiles_per_image, sm_count(), /*shared_table=*/true);
     const HeadEpi epi{dec1, dec2, energy, C, (int)hw};
     const size_t smem = pixel_gemm_smem(K, HG_N);
 #define HG_LAUNCH(S)                                                                                                  \

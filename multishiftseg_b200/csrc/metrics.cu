@@ -22,12 +22,17 @@
 namespace mss {
 
 constexpr int CT_THREADS = 256;
-constexpr int CT_IPT = 8;
-constexpr int CT_TILE = CT_THREADS * CT_IPT;  // 2048
 
 // block-wide exclusive scan of one count per thread; CTA total in `tot`
+// BAR = 0: __syncthreads (every thread of the CTA takes part); BAR > 0: named barrier over the first THREADS threads (the
+// CTA also has a walker warp that must not be waited for)
+template <int THREADS = CT_THREADS, int BAR = 0>
+__device__ __forceinline__ void scan_barrier() {
+    if (BAR == 0) __syncthreads(); else named_barrier(BAR, THREADS);
+}
+template <int THREADS = CT_THREADS, int BAR = 0>
 __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned &tot) {
-    __shared__ unsigned s_w[CT_THREADS / 32];
+    __shared__ unsigned s_w[THREADS / 32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned inc = v;
 #pragma unroll
@@ -36,16 +41,16 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned &t
         if (lane >= d) inc += t;
     }
     if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
+    scan_barrier<THREADS, BAR>();
     unsigned base = 0, all = 0;
 #pragma unroll
-    for (int w = 0; w < CT_THREADS / 32; w++) {
+    for (int w = 0; w < THREADS / 32; w++) {
         const unsigned x = s_w[w];
         if (w < (int)warp) base += x;
         all += x;
     }
     tot = all;
-    __syncthreads();
+    scan_barrier<THREADS, BAR>();
     return base + inc - v;
 }
 
@@ -62,37 +67,58 @@ __device__ __forceinline__ long long merge_path(const uint32_t *__restrict__ A, 
     return lo;
 }
 
-// one thread per tile boundary: a_start[t] = merge path at diagonal min(t * CT_TILE, nA + nB), t = 0 .. tiles_upper
+constexpr int MC_THREADS = 256;
+constexpr int MC_IPT = 16;
+constexpr int MC_TILE = MC_THREADS * MC_IPT;   // 4096 merged keys per CTA: half as many look-backs as 2048
+
+// one thread per tile boundary: a_start[t] = merge path at diagonal min(t * MC_TILE, nA + nB), t = 0 .. tiles_upper
 __global__ void __launch_bounds__(256)
 merge_partition_kernel(const SortPlan *__restrict__ plan, long long *__restrict__ a_start, long long tiles_upper) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > tiles_upper) return;
     const long long nA = plan->seg[0].n, nB = plan->seg[1].n;
-    const long long diag = min(t * CT_TILE, nA + nB);
+    const long long diag = min(t * MC_TILE, nA + nB);
     a_start[t] = merge_path(plan->seg[0].x, nA, plan->seg[1].x, nB, diag);
 }
 
-// totals[0] = T (distinct keys), written by the last tile
-__global__ void __launch_bounds__(CT_THREADS)
+// totals[0] = T (distinct keys), written by the last tile.
+// A threshold is staged as two 16-bit tile-local numbers (negatives consumed, merged position) and widened to the int64
+// (tps, fps) pair only in the coalesced write-out.
+__global__ void __launch_bounds__(MC_THREADS + 32)
 merge_counts_kernel(const SortPlan *__restrict__ plan, const long long *__restrict__ a_start, long long pos_before,
                     long long neg_before, long long *__restrict__ tps, long long *__restrict__ fps,
                     unsigned long long *status, unsigned *counter, unsigned long long *__restrict__ totals) {
-    __shared__ uint32_t s_k[CT_TILE];
-    __shared__ long long s_t[CT_TILE], s_f[CT_TILE];
-    __shared__ unsigned s_tile;
+    __shared__ uint32_t s_k[MC_TILE];
+    __shared__ unsigned short s_a[MC_TILE], s_p[MC_TILE];
+    __shared__ unsigned s_tile, s_tot;
     __shared__ unsigned long long s_excl;
     const unsigned tid = threadIdx.x;
-    if (tid == 0) s_tile = atomicAdd(counter, 1u);       // tiles in start order: the look-back never waits on a tile not yet running
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);       // tiles in start order: a walk never waits on a tile not yet running
     __syncthreads();
     const unsigned tile = s_tile;
-    const uint32_t *__restrict__ A = plan->seg[0].x, *__restrict__ B = plan->seg[1].x;
     const long long nA = plan->seg[0].n, nB = plan->seg[1].n, M = nA + nB;
-    const long long tiles = (M + CT_TILE - 1) / CT_TILE;
+    const long long tiles = (M + MC_TILE - 1) / MC_TILE;
     if ((long long)tile >= tiles) return;
-    const long long d0 = (long long)tile * CT_TILE, d1 = min(M, d0 + CT_TILE);
+    if (tid >= MC_THREADS) {
+        // ---- walker warp: the exclusive prefix, while the workers merge
+        const unsigned long long ex = tile_walk(status, tile);
+        __syncthreads();                                                  // (A) the tile's count is known
+        if (tid == MC_THREADS) {
+            tile_publish_inclusive(status, tile, ex + s_tot);
+            s_excl = ex;
+            if ((long long)tile == tiles - 1) totals[0] = ex + s_tot;
+        }
+        __syncthreads();                                                  // (B)
+        return;
+    }
+    const uint32_t *__restrict__ A = plan->seg[0].x, *__restrict__ B = plan->seg[1].x;
+    const long long d0 = (long long)tile * MC_TILE, d1 = min(M, d0 + MC_TILE);
     const long long a0 = a_start[tile], a1 = a_start[tile + 1], b0 = d0 - a0, b1 = d1 - a1;
     const int na = (int)(a1 - a0), nb = (int)(b1 - b0), cnt = na + nb;
-    for (int i = tid; i < cnt; i += CT_THREADS) s_k[i] = (i < na) ? __ldg(A + a0 + i) : __ldg(B + b0 + (i - na));
+    {
+        const uint32_t *pa = A + a0, *pb = B + b0 - na;
+        for (int i = tid; i < cnt; i += MC_THREADS) s_k[i] = (i < na) ? __ldg(pa + i) : __ldg(pb + i);
+    }
     // the key that follows this tile in the merged order (decides whether the tile's last key ends a run)
     const bool has_next = d1 < M;
     uint32_t nxt = 0;
@@ -100,10 +126,10 @@ merge_counts_kernel(const SortPlan *__restrict__ plan, const long long *__restri
         const uint32_t ka = (a1 < nA) ? __ldg(A + a1) : 0xFFFFFFFFu, kb = (b1 < nB) ? __ldg(B + b1) : 0xFFFFFFFFu;
         nxt = (a1 < nA && b1 < nB) ? min(ka, kb) : (a1 < nA ? ka : kb);
     }
-    __syncthreads();
+    named_barrier(1, MC_THREADS);
 
-    // this thread's CT_IPT keys of the merged order start at diagonal `diag` of the tile
-    const int diag = min((int)tid * CT_IPT, cnt);
+    // this thread's MC_IPT keys of the merged order start at diagonal `diag` of the tile
+    const int diag = min((int)tid * MC_IPT, cnt);
     int lo = max(0, diag - nb), hi = min(diag, na);
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -111,52 +137,53 @@ merge_counts_kernel(const SortPlan *__restrict__ plan, const long long *__restri
     }
     int ai = lo, bi = diag - lo;
     const int ai0 = ai;
-    unsigned took_a = 0, ends = 0, n_end = 0;
+    unsigned took_a = 0, ends = 0;
     {
-        bool ta = (bi >= nb) || (ai < na && s_k[ai] <= s_k[na + bi]);
-        uint32_t key = (diag < cnt) ? (ta ? s_k[ai] : s_k[na + bi]) : 0u;
+        // heads of the two runs in registers; only the consumed one is re-read
+        uint32_t ka = (ai < na) ? s_k[ai] : 0u, kb = (bi < nb) ? s_k[na + bi] : 0u;
+        bool ta = (bi >= nb) || (ai < na && ka <= kb);
+        uint32_t key = ta ? ka : kb;
 #pragma unroll
-        for (int j = 0; j < CT_IPT; j++) {
+        for (int j = 0; j < MC_IPT; j++) {
             const int p = diag + j;
             if (p < cnt) {
-                if (ta) { ai++; took_a |= 1u << j; } else bi++;
+                if (ta) { ai++; took_a |= 1u << j; if (ai < na) ka = s_k[ai]; }
+                else { bi++; if (bi < nb) kb = s_k[na + bi]; }
                 bool end;
                 if (p + 1 < cnt) {
-                    ta = (bi >= nb) || (ai < na && s_k[ai] <= s_k[na + bi]);
-                    const uint32_t nk = ta ? s_k[ai] : s_k[na + bi];
+                    ta = (bi >= nb) || (ai < na && ka <= kb);
+                    const uint32_t nk = ta ? ka : kb;
                     end = nk != key;
                     key = nk;
                 } else {
                     end = !has_next || nxt != key;
                 }
-                if (end) { ends |= 1u << j; n_end++; }
+                if (end) ends |= 1u << j;
             }
         }
     }
     unsigned tot;
-    unsigned slot = block_exclusive_scan(n_end, tot);
+    unsigned slot = block_exclusive_scan<MC_THREADS, 1>(__popc(ends), tot);
+    if (tid == 0) {
+        tile_publish_aggregate(status, tile, tot);       // the successors' walkers can use it long before our own walk ends
+        s_tot = tot;
+    }
 #pragma unroll
-    for (int j = 0; j < CT_IPT; j++) {
+    for (int j = 0; j < MC_IPT; j++) {
         if ((ends >> j) & 1u) {
-            const int aj = ai0 + __popc(took_a & ((2u << j) - 1u));      // negatives consumed up to and including item j
-            const int bj = diag + j + 1 - aj;
-            s_t[slot] = pos_before + b0 + bj;
-            s_f[slot] = neg_before + a0 + aj;
+            s_a[slot] = (unsigned short)(ai0 + __popc(took_a & ((2u << j) - 1u)));   // negatives consumed up to and including item j
+            s_p[slot] = (unsigned short)(diag + j + 1);                              // merged keys consumed (<= 4096)
             slot++;
         }
     }
-    if (tid < 32) {
-        const unsigned long long ex = warp_lookback(status, tile, tot);
-        if (tid == 0) {
-            s_excl = ex;
-            if ((long long)tile == tiles - 1) totals[0] = ex + tot;
-        }
-    }
-    __syncthreads();
-    const unsigned long long ex = s_excl;
-    for (unsigned q = tid; q < tot; q += CT_THREADS) {
-        tps[ex + q] = s_t[q];
-        fps[ex + q] = s_f[q];
+    __syncthreads();                                                      // (A)
+    __syncthreads();                                                      // (B) the walker has stored the prefix
+    long long *__restrict__ tp = tps + s_excl, *__restrict__ fp = fps + s_excl;
+    const long long tb = pos_before + b0, fb = neg_before + a0;
+    for (unsigned q = tid; q < tot; q += MC_THREADS) {
+        const int aj = s_a[q], pj = s_p[q];
+        tp[q] = tb + (pj - aj);
+        fp[q] = fb + aj;
     }
 }
 
@@ -171,17 +198,18 @@ __device__ __forceinline__ Best better(Best x, Best y) {
     if (y.d < x.d || (y.d == x.d && y.k > x.k)) return y;
     return x;
 }
+template <int THREADS = CT_THREADS, int BAR = 0>
 __device__ __forceinline__ Best block_best(Best b) {      // valid in thread 0
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         Best o{__shfl_xor_sync(0xffffffffu, b.d, s), __shfl_xor_sync(0xffffffffu, b.k, s)};
         b = better(b, o);
     }
-    __shared__ Best sb[CT_THREADS / 32];
+    __shared__ Best sb[THREADS / 32];
     if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = b;
-    __syncthreads();
+    scan_barrier<THREADS, BAR>();
     if (threadIdx.x == 0)
-        for (int w = 1; w < CT_THREADS / 32; w++) b = better(b, sb[w]);
+        for (int w = 1; w < THREADS / 32; w++) b = better(b, sb[w]);
     return b;
 }
 
@@ -190,27 +218,31 @@ __device__ __forceinline__ long long load_T(const unsigned long long *d_T, long 
     return d_T ? (long long)*d_T : T_host;
 }
 
-// Single pass: one thread owns thresholds [i0, i0+8) and needs (tps, fps) at i0-1 .. i0+8; kept points are written
-// at the offset a decoupled look-back delivers; the FPR95 candidate of the tile goes to tile_best[tile].
-// totals_out[0] = number of kept points (written by the last tile).
-__global__ void __launch_bounds__(CT_THREADS)
-roc_compact_kernel(const long long *__restrict__ tps, const long long *__restrict__ fps, const unsigned long long *d_T,
-                   long long T_host, double recall_level, unsigned long long *status, unsigned *counter,
-                   Best *__restrict__ tile_best, long long *__restrict__ tps_k, long long *__restrict__ fps_k,
-                   unsigned long long *__restrict__ totals_out) {
-    __shared__ unsigned s_tile;
-    __shared__ unsigned long long s_excl;
-    if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
-    __syncthreads();
-    const unsigned tile = s_tile;
-    const long long T = load_T(d_T, T_host);
-    const long long tiles = (T + CT_TILE - 1) / CT_TILE;
-    if ((long long)tile >= tiles) return;
-    const long long i0 = (long long)tile * CT_TILE + (long long)threadIdx.x * CT_IPT;
-    long long t[CT_IPT + 2], f[CT_IPT + 2];                  // window index w <-> threshold i0 - 1 + w
-    if (i0 + CT_IPT <= T && ((((uintptr_t)tps) | ((uintptr_t)fps)) & 15) == 0) {
+// Single pass over DRAM, fat tiles: a CTA owns up to 16384 consecutive thresholds as `sub` <= RC_SUB sub-tiles of
+// 256 x 4 thresholds (the host picks `sub` so that small inputs still fill the GPU).
+//   phase A  per sub-tile: keep flags (second differences over a window i0-1 .. i0+4, the neighbours' values by
+//            shuffle) and the FPR95 candidate -- a pure streaming loop, no barrier inside, so the loads of several
+//            sub-tiles are in flight; the 4-bit keep masks stay in one 64-bit register;
+//   offsets  ONE multi-scan for all sub-tiles at the end: nibble popcounts by SWAR, byte-packed warp scans (16 counters in
+//            two 64-bit words), a 128-entry (sub-tile, warp) table scanned by one warp -- two barriers per tile;
+//   walk     a dedicated warp computes the exclusive prefix over the previous tiles meanwhile (one look-back per tile);
+//   phase B  the tile is read again -- from L2, the CTAs of one wave hold < 80 MB -- and the kept points are written at
+//            their final offsets.
+// History (round 2, T = 67 M): 256 x 8 thresholds per CTA with warp 0 walking after the scan 1.20 ms (9 polls of ~0.5 us
+// per tile, 55 % of the stall samples on the barrier behind the walk); 16384-threshold tiles with a scan per sub-tile
+// 0.88 ms (latency-bound: a load round trip and two barriers per sub-tile); this form: see profiles/.
+// totals_out[0] = number of kept points (written by the last tile); tile_best[tile] = FPR95 candidate of the tile.
+constexpr int RC_THREADS = 256;
+constexpr int RC_IPT = 4;
+constexpr int RC_SUB = 16;
+constexpr int RC_SUBTILE = RC_THREADS * RC_IPT;           // 1024 thresholds
+constexpr int CT_TILE_MAX = RC_SUBTILE * RC_SUB;          // 16384 thresholds per ROC / FPR95 tile at most
+
+__device__ __forceinline__ void roc_load4(const long long *__restrict__ tps, const long long *__restrict__ fps, long long i0,
+                                          long long T, long long (&t)[RC_IPT + 2], long long (&f)[RC_IPT + 2]) {
+    if (i0 + RC_IPT <= T && ((((uintptr_t)tps) | ((uintptr_t)fps)) & 15) == 0) {
 #pragma unroll
-        for (int j = 0; j < CT_IPT; j += 2) {
+        for (int j = 0; j < RC_IPT; j += 2) {
             const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(tps + i0 + j));
             const longlong2 c = __ldg(reinterpret_cast<const longlong2 *>(fps + i0 + j));
             t[j + 1] = a.x; t[j + 2] = a.y;
@@ -218,71 +250,157 @@ roc_compact_kernel(const long long *__restrict__ tps, const long long *__restric
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < CT_IPT; j++) {
+        for (int j = 0; j < RC_IPT; j++) {
             const bool in = i0 + j < T;
             t[j + 1] = in ? __ldg(tps + i0 + j) : 0;
             f[j + 1] = in ? __ldg(fps + i0 + j) : 0;
         }
     }
-    t[0] = (i0 > 0 && i0 - 1 < T) ? __ldg(tps + i0 - 1) : 0;
-    f[0] = (i0 > 0 && i0 - 1 < T) ? __ldg(fps + i0 - 1) : 0;
-    t[CT_IPT + 1] = (i0 + CT_IPT < T) ? __ldg(tps + i0 + CT_IPT) : 0;
-    f[CT_IPT + 1] = (i0 + CT_IPT < T) ? __ldg(fps + i0 + CT_IPT) : 0;
+}
 
-    unsigned keep = 0, cnt = 0;
-#pragma unroll
-    for (int j = 0; j < CT_IPT; j++) {
-        const long long k = i0 + j;
-        if (k < T) {
-            bool kp = true;
-            if (T > 2 && k != 0 && k != T - 1) {
-                const long long d2f = f[j + 2] - 2 * f[j + 1] + f[j];
-                const long long d2t = t[j + 2] - 2 * t[j + 1] + t[j];
-                kp = d2f != 0 || d2t != 0;
-            }
-            if (kp) { keep |= 1u << j; cnt++; }
-        }
-    }
-    unsigned tot;
-    const unsigned ex = block_exclusive_scan(cnt, tot);
-    // FPR95 candidate of this tile
-    {
-        const double P = (double)__ldg(tps + T - 1);
-        Best b{INFINITY, -1};
-#pragma unroll
-        for (int j = 0; j < CT_IPT; j++) {
-            const long long k = i0 + j;
-            if (k < T && (k == 0 || (double)t[j] != P)) {     // k <= searchsorted(tps, tps[-1])
-                const double d = fabs(__dsub_rn(__ddiv_rn((double)t[j + 1], P), recall_level));
-                b = better(b, Best{d, k});
-            }
-        }
-        b = block_best(b);
-        if (threadIdx.x == 0) tile_best[tile] = b;
-    }
-    if (threadIdx.x < 32) {
-        const unsigned long long e = warp_lookback(status, tile, tot);
-        if (threadIdx.x == 0) {
-            s_excl = e;
-            if ((long long)tile == tiles - 1) totals_out[0] = e + tot;
-        }
-    }
+__global__ void __launch_bounds__(RC_THREADS + 32)
+roc_compact_kernel(const long long *__restrict__ tps, const long long *__restrict__ fps, const unsigned long long *d_T,
+                   long long T_host, int sub, double recall_level, unsigned long long *status, unsigned *counter,
+                   Best *__restrict__ tile_best, long long *__restrict__ tps_k, long long *__restrict__ fps_k,
+                   unsigned long long *__restrict__ totals_out) {
+    __shared__ unsigned s_tile, s_tot;
+    __shared__ unsigned long long s_excl;
+    __shared__ unsigned char s_wt[RC_SUB][RC_THREADS / 32];      // kept points of (sub-tile, warp)
+    __shared__ unsigned short s_base[RC_SUB][RC_THREADS / 32];   // their exclusive prefix in (sub-tile, warp) order
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);
     __syncthreads();
-    unsigned long long o = s_excl + ex;
+    const unsigned tile = s_tile;
+    const long long T = load_T(d_T, T_host);
+    const long long tile_thr = (long long)sub * RC_SUBTILE;
+    const long long tiles = (T + tile_thr - 1) / tile_thr;
+    if ((long long)tile >= tiles) return;
+    if (tid >= RC_THREADS) {
+        const unsigned long long ex = tile_walk(status, tile);
+        __syncthreads();                                                  // (A) the tile's count is known
+        if (tid == RC_THREADS) {
+            tile_publish_inclusive(status, tile, ex + s_tot);
+            s_excl = ex;
+            if ((long long)tile == tiles - 1) totals_out[0] = ex + s_tot;
+        }
+        __syncthreads();                                                  // (B)
+        return;
+    }
+    const unsigned lane = tid & 31, warp = tid >> 5;
+    const long long tile0 = (long long)tile * tile_thr;
+    const double P = (double)__ldg(tps + T - 1);
+    unsigned long long masks = 0;                  // 4 keep bits per sub-tile
+    Best best{INFINITY, -1};
+#pragma unroll 2
+    for (int sb = 0; sb < sub; sb++) {
+        const long long i0 = tile0 + (long long)sb * RC_SUBTILE + (long long)tid * RC_IPT;
+        long long t[RC_IPT + 2], f[RC_IPT + 2];                  // window index w <-> threshold i0 - 1 + w
+        roc_load4(tps, fps, i0, T, t, f);
+        // the neighbours' values travel by shuffle; only the warp's edge lanes read them from memory
+        {
+            const long long tl = __shfl_up_sync(0xffffffffu, t[RC_IPT], 1), fl = __shfl_up_sync(0xffffffffu, f[RC_IPT], 1);
+            const long long tr = __shfl_down_sync(0xffffffffu, t[1], 1), fr = __shfl_down_sync(0xffffffffu, f[1], 1);
+            if (lane == 0) {
+                t[0] = (i0 > 0 && i0 - 1 < T) ? __ldg(tps + i0 - 1) : 0;
+                f[0] = (i0 > 0 && i0 - 1 < T) ? __ldg(fps + i0 - 1) : 0;
+            } else { t[0] = tl; f[0] = fl; }
+            if (lane == 31) {
+                t[RC_IPT + 1] = (i0 + RC_IPT < T) ? __ldg(tps + i0 + RC_IPT) : 0;
+                f[RC_IPT + 1] = (i0 + RC_IPT < T) ? __ldg(fps + i0 + RC_IPT) : 0;
+            } else { t[RC_IPT + 1] = tr; f[RC_IPT + 1] = fr; }
+        }
+        unsigned keep = 0;
 #pragma unroll
-    for (int j = 0; j < CT_IPT; j++) {
-        if ((keep >> j) & 1u) {
-            tps_k[o] = t[j + 1];
-            fps_k[o] = f[j + 1];
-            o++;
+        for (int j = 0; j < RC_IPT; j++) {
+            const long long k = i0 + j;
+            if (k < T) {
+                bool kp = true;
+                if (T > 2 && k != 0 && k != T - 1) {
+                    const long long d2f = f[j + 2] - 2 * f[j + 1] + f[j];
+                    const long long d2t = t[j + 2] - 2 * t[j + 1] + t[j];
+                    kp = d2f != 0 || d2t != 0;
+                }
+                if (kp) keep |= 1u << j;
+                if (k == 0 || (double)t[j] != P) {     // FPR95: k <= searchsorted(tps, tps[-1])
+                    const double d = fabs(__dsub_rn(__ddiv_rn((double)t[j + 1], P), recall_level));
+                    best = better(best, Best{d, k});
+                }
+            }
+        }
+        masks |= (unsigned long long)keep << (4 * sb);
+    }
+    // ---- offsets of all sub-tiles at once.  Nibble popcounts (SWAR): nibble sb of `pc` = kept points of sub-tile sb.
+    unsigned long long pc = masks - ((masks >> 1) & 0x5555555555555555ull);
+    pc = (pc & 0x3333333333333333ull) + ((pc >> 2) & 0x3333333333333333ull);
+    // bytes: word e holds the even sub-tiles (byte q <-> sub-tile 2q), word o the odd ones; inclusive warp scans
+    // (a warp keeps <= 128 points of a sub-tile: fits a byte)
+    unsigned long long e = pc & 0x0F0F0F0F0F0F0F0Full, o = (pc >> 4) & 0x0F0F0F0F0F0F0F0Full;
+    const unsigned long long own_e = e, own_o = o;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long te = __shfl_up_sync(0xffffffffu, e, d), to = __shfl_up_sync(0xffffffffu, o, d);
+        if (lane >= (unsigned)d) { e += te; o += to; }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int q = 0; q < RC_SUB / 2; q++) {
+            s_wt[2 * q][warp] = (unsigned char)(e >> (8 * q));
+            s_wt[2 * q + 1][warp] = (unsigned char)(o >> (8 * q));
+        }
+    }
+    best = block_best<RC_THREADS, 1>(best);                              // (contains a worker barrier: s_wt is complete after it)
+    if (tid == 0) tile_best[tile] = best;
+    if (warp == 0) {
+        // 128 (sub-tile, warp) counts in sub-tile-major order, 4 per lane
+        const unsigned char *w = &s_wt[0][0] + lane * 4;
+        const unsigned c0 = w[0], c1 = w[1], c2 = w[2], c3 = w[3];
+        unsigned inc = c0 + c1 + c2 + c3;
+        const unsigned sum = inc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned tt = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (unsigned)d) inc += tt;
+        }
+        unsigned short *bo = &s_base[0][0] + lane * 4;
+        const unsigned x0 = inc - sum;
+        bo[0] = (unsigned short)x0; bo[1] = (unsigned short)(x0 + c0); bo[2] = (unsigned short)(x0 + c0 + c1);
+        bo[3] = (unsigned short)(x0 + c0 + c1 + c2);
+        if (lane == 31) {
+            tile_publish_aggregate(status, tile, inc);
+            s_tot = inc;
+        }
+    }
+    __syncthreads();                                                      // (A)
+    __syncthreads();                                                      // (B) the walker has stored the prefix
+    const unsigned long long base = s_excl;
+    e -= own_e;                                                           // exclusive inside the warp
+    o -= own_o;
+#pragma unroll 2
+    for (int sb = 0; sb < sub; sb++) {
+        const unsigned keep = (unsigned)(masks >> (4 * sb)) & 15u;
+        if (keep) {
+            const long long i0 = tile0 + (long long)sb * RC_SUBTILE + (long long)tid * RC_IPT;
+            long long t[RC_IPT + 2], f[RC_IPT + 2];
+            roc_load4(tps, fps, i0, T, t, f);                      // second read of the tile: L2
+            const unsigned in_warp = (unsigned)(((sb & 1) ? o : e) >> (8 * (sb >> 1))) & 255u;
+            unsigned long long op = base + s_base[sb][warp] + in_warp;
+#pragma unroll
+            for (int j = 0; j < RC_IPT; j++) {
+                if ((keep >> j) & 1u) {
+                    tps_k[op] = t[j + 1];
+                    fps_k[op] = f[j + 1];
+                    op++;
+                }
+            }
         }
     }
 }
 
 // reduce the tile candidates to gridDim.x candidates (grid-stride)
 __global__ void __launch_bounds__(CT_THREADS)
-fpr_reduce_kernel(const Best *__restrict__ in, const unsigned long long *d_T, long long T_host, Best *__restrict__ out) {
-    const long long T = load_T(d_T, T_host), n = (T + CT_TILE - 1) / CT_TILE;
+fpr_reduce_kernel(const Best *__restrict__ in, const unsigned long long *d_T, long long T_host, long long tile_thr,
+                  Best *__restrict__ out) {
+    const long long T = load_T(d_T, T_host), n = (T + tile_thr - 1) / tile_thr;
     Best b{INFINITY, -1};
     for (long long i = (long long)blockIdx.x * CT_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * CT_THREADS)
         b = better(b, in[i]);
@@ -293,9 +411,9 @@ fpr_reduce_kernel(const Best *__restrict__ in, const unsigned long long *d_T, lo
 // n_partial > 0: `cand` holds n_partial reduced candidates; else it holds one candidate per tile
 __global__ void __launch_bounds__(CT_THREADS)
 fpr_final_kernel(const Best *__restrict__ cand, int n_partial, const long long *__restrict__ fps,
-                 const unsigned long long *d_T, long long T_host, double *__restrict__ out) {
+                 const unsigned long long *d_T, long long T_host, long long tile_thr, double *__restrict__ out) {
     const long long T = load_T(d_T, T_host);
-    const long long n = n_partial > 0 ? n_partial : (T + CT_TILE - 1) / CT_TILE;
+    const long long n = n_partial > 0 ? n_partial : (T + tile_thr - 1) / tile_thr;
     Best b{INFINITY, -1};
     for (long long i = threadIdx.x; i < n; i += CT_THREADS) b = better(b, cand[i]);
     b = block_best(b);
@@ -422,6 +540,22 @@ __device__ __forceinline__ void leaf_sum_body(const Term &term, const long long 
     if (live && sub == 0) leaf_sum[leaf] = res;
 }
 
+// Leaf sums of both integrals.  A CTA owns LS_LEAVES consecutive leaves (<= 128 terms each), i.e. ONE contiguous range of
+// thresholds: it is staged into shared memory as float64 by coalesced loads issued all at once (the first form read
+// tps[k] / fps[k] per term inside the summation loop and ncu showed 70 % of the stall samples waiting on those loads,
+// issue 27 %, DRAM 21 %), then 8 lanes per leaf -- numpy's 8 interleaved accumulators -- sum from shared memory.
+// Neighbouring terms share float64 quotients (AP term j needs rec[k] and rec[k-1], the ROC term needs point j and point
+// j-1): a lane computes only ITS OWN quotients and takes the neighbour's through a shuffle -- 2 instead of 3 resp. 4
+// float64 divides per term; values and operation order per term are unchanged, hence so is every bit of the sums.
+//   AP : lane sub of block i owns k = K0 - i - sub; rec[k-1] is lane sub+1's value, and for lane 7 lane 0's value of the
+//        NEXT block, which is computed one block ahead anyway.
+//   ROC: lane sub owns point j; point j-1 is lane sub-1's value, and for lane 0 lane 7's value of the previous block.
+constexpr int LS_THREADS = 256;
+constexpr int LS_LEAVES = LS_THREADS / 8;                 // 32 leaves per CTA
+constexpr int LS_MAX_TERMS = LS_LEAVES * 128;             // 4096
+constexpr int LS_STAGE = LS_MAX_TERMS + 8;                // + the neighbour point
+constexpr int LS_SMEM = 2 * LS_STAGE * 8;
+
 // blockIdx.y = 0: AP leaves, 1: ROC leaves (one launch for both sums)
 struct LeafJob {
     ApTerm ap;
@@ -430,15 +564,113 @@ struct LeafJob {
     long long n_leaves[2];
     double *leaf_sum[2];
 };
-__global__ void __launch_bounds__(256)
+
+__global__ void __launch_bounds__(LS_THREADS)
 leaf_sum_kernel(LeafJob job) {
-    if (blockIdx.y == 0) {
-        if ((long long)blockIdx.x * 32 >= job.n_leaves[0]) return;
-        leaf_sum_body(job.ap, job.leaf_start[0], job.n_leaves[0], job.leaf_sum[0]);
+    extern __shared__ __align__(16) double s_stage[];
+    double *s_t = s_stage, *s_f = s_stage + LS_STAGE;
+    const int y = blockIdx.y;
+    const long long n_leaves = job.n_leaves[y];
+    const long long first = (long long)blockIdx.x * LS_LEAVES;
+    if (first >= n_leaves) return;
+    const long long *__restrict__ leaf_start = job.leaf_start[y];
+    const long long last = min(first + LS_LEAVES, n_leaves);
+    const long long S0 = leaf_start[first], S1 = leaf_start[last];          // terms [S0, S1) of this CTA
+    const unsigned tid = threadIdx.x, sub = tid & 7;
+    const unsigned gmask = 0xffu << (tid & 24);     // the 8 lanes of this leaf: leaves of one warp differ in length
+    const long long leaf = first + (tid >> 3);
+    const bool live = leaf < last;
+    const long long s = live ? leaf_start[leaf] : S0;
+    const long long m = live ? leaf_start[leaf + 1] - s : 0;
+    double res = -0.0;
+    if (y == 0) {
+        // ---- AP: term j <-> threshold k = T-1-j; staged thresholds k in [klo, khi], khi = T-1-S0, klo = T-1-S1 (>= -1)
+        const ApTerm &term = job.ap;
+        const long long T = term.T, klo = T - 1 - S1, khi = T - 1 - S0;
+        for (long long q = tid; q <= khi - klo; q += LS_THREADS) {
+            const long long k = klo + q;
+            s_t[q] = k >= 0 ? (double)__ldg(term.tps + k) : 0.0;
+            s_f[q] = k >= 0 ? (double)__ldg(term.fps + k) : 0.0;
+        }
+        const double P = (double)__ldg(term.tps + T - 1);
+        __syncthreads();
+        // rec[-1] := 0 (the appended (1, 0) point of precision_recall_curve)
+        // (k = -1 is staged as 0, and 0 / P = +0; k < klo only occurs for the look-ahead of lanes that do not use it)
+        auto rec = [&](long long k) { return k >= klo ? __ddiv_rn(s_t[k - klo], P) : 0.0; };
+        auto termv = [&](long long j) {
+            const long long k = T - 1 - j;
+            const double t = s_t[k - klo], f = s_f[k - klo];
+            return __dmul_rn(__dsub_rn(rec(k - 1), rec(k)), __ddiv_rn(t, __dadd_rn(t, f)));
+        };
+        if (m < 8) {
+            if (sub == 0)
+                for (long long i = 0; i < m; i++) res = __dadd_rn(res, termv(s + i));
+        } else {
+            const long long body = m - (m & 7);
+            const long long K0 = T - 1 - s - sub;                        // this lane's k in block 0
+            double r_cur = rec(K0), r = 0.0;
+            for (long long i = 0; i < body; i += 8) {
+                const double r_next = rec(K0 - i - 8);                   // next block's own quotient
+                double r_prev = __shfl_down_sync(gmask, r_cur, 1, 8);
+                const double r_wrap = __shfl_sync(gmask, r_next, 0, 8);
+                if (sub == 7) r_prev = r_wrap;
+                const long long k = K0 - i;
+                const double t = s_t[k - klo], f = s_f[k - klo];
+                const double v = __dmul_rn(__dsub_rn(r_prev, r_cur), __ddiv_rn(t, __dadd_rn(t, f)));
+                r = (i == 0) ? v : __dadd_rn(r, v);
+                r_cur = r_next;
+            }
+            // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) -- fp addition is commutative, so the butterfly is exact
+            r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+            r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+            r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+            res = r;
+            if (sub == 0)
+                for (long long i = body; i < m; i++) res = __dadd_rn(res, termv(s + i));
+        }
     } else {
-        if ((long long)blockIdx.x * 32 >= job.n_leaves[1]) return;
-        leaf_sum_body(job.roc, job.leaf_start[1], job.n_leaves[1], job.leaf_sum[1]);
+        // ---- ROC: term j joins points j-1 and j of the kept curve (point -1 = the origin); staged points [S0-1, S1-1]
+        const RocTerm &term = job.roc;
+        const long long jlo = S0 - 1;
+        for (long long q = tid; q <= S1 - 1 - jlo; q += LS_THREADS) {
+            const long long j = jlo + q;
+            s_t[q] = j >= 0 ? (double)__ldg(term.tps_k + j) : 0.0;
+            s_f[q] = j >= 0 ? (double)__ldg(term.fps_k + j) : 0.0;
+        }
+        const double P = (double)__ldg(term.p_P), N = (double)__ldg(term.p_N);
+        __syncthreads();
+        auto termv = [&](long long j) {
+            const double f1 = __ddiv_rn(s_f[j - jlo], N), t1 = __ddiv_rn(s_t[j - jlo], P);
+            const double f0 = __ddiv_rn(s_f[j - 1 - jlo], N), t0 = __ddiv_rn(s_t[j - 1 - jlo], P);
+            return __ddiv_rn(__dmul_rn(__dsub_rn(f1, f0), __dadd_rn(t1, t0)), 2.0);
+        };
+        if (m < 8) {
+            if (sub == 0)
+                for (long long i = 0; i < m; i++) res = __dadd_rn(res, termv(s + i));
+        } else {
+            const long long body = m - (m & 7);
+            // point s - 1: needed by lane 0 of the first block only
+            double f_carry = __ddiv_rn(s_f[s - 1 - jlo], N), t_carry = __ddiv_rn(s_t[s - 1 - jlo], P);
+            double r = 0.0;
+            for (long long i = 0; i < body; i += 8) {
+                const long long j = s + i + sub;
+                const double f1 = __ddiv_rn(s_f[j - jlo], N), t1 = __ddiv_rn(s_t[j - jlo], P);
+                double f0 = __shfl_up_sync(gmask, f1, 1, 8), t0 = __shfl_up_sync(gmask, t1, 1, 8);
+                if (sub == 0) { f0 = f_carry; t0 = t_carry; }
+                const double v = __ddiv_rn(__dmul_rn(__dsub_rn(f1, f0), __dadd_rn(t1, t0)), 2.0);
+                r = (i == 0) ? v : __dadd_rn(r, v);
+                f_carry = __shfl_sync(gmask, f1, 7, 8);                  // lane 7's point is lane 0's predecessor next block
+                t_carry = __shfl_sync(gmask, t1, 7, 8);
+            }
+            r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+            r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+            r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+            res = r;
+            if (sub == 0)
+                for (long long i = body; i < m; i++) res = __dadd_rn(res, termv(s + i));
+        }
     }
+    if (live && sub == 0) job.leaf_sum[y][leaf] = res;
 }
 
 // The tree above the leaves.  The host cuts it at "frontier" nodes (the first node on each root path
@@ -561,7 +793,8 @@ struct PwDevice {
     double *node_sum;
 };
 
-static size_t ct_tiles(int64_t n) { return (size_t)((n + CT_TILE - 1) / CT_TILE); }
+static size_t ct_tiles(int64_t n) { return (size_t)((n + RC_SUBTILE - 1) / RC_SUBTILE); }    // sizing bound: one sub-tile per tile
+static size_t mc_tiles(int64_t n) { return (size_t)((n + MC_TILE - 1) / MC_TILE); }
 
 // ---- counting stage ----------------------------------------------------------------------------------
 struct CountsWs {
@@ -575,7 +808,7 @@ struct CountsWs {
 };
 static bool carve_counts(void *ws, size_t bytes, int64_t n_upper, CountsWs &o) {
     Carver c(ws, bytes);
-    o.tiles_upper = ct_tiles(n_upper);
+    o.tiles_upper = mc_tiles(n_upper);
     o.plan = c.take<SortPlan>(1);
     o.a_start = c.take<long long>(o.tiles_upper + 1);
     o.counter = c.take<unsigned>(64);
@@ -587,7 +820,7 @@ static bool carve_counts(void *ws, size_t bytes, int64_t n_upper, CountsWs &o) {
 }
 static size_t counts_ws_bytes(int64_t n) {
     if (n < 0) n = 0;
-    return 256 + align_up((ct_tiles(n) + 1) * 8, 256) + 256 + 256 + align_up((ct_tiles(n) + 1) * 8, 256) + 1024;
+    return 256 + align_up((mc_tiles(n) + 1) * 8, 256) + 256 + 256 + align_up((mc_tiles(n) + 1) * 8, 256) + 1024;
 }
 
 // merge the plan's two sorted streams into per-threshold cumulative counts; T lands in w.totals[0] (device)
@@ -598,7 +831,7 @@ static int counts_enqueue(const SortPlan *plan, int64_t n_upper, int64_t pos_bef
     if (w.tiles_upper == 0) return MSS_OK;
     merge_partition_kernel<<<(unsigned)((w.tiles_upper + 1 + 255) / 256), 256, 0, st>>>(plan, w.a_start, (long long)w.tiles_upper);
     MSS_CHECK_LAUNCH();
-    merge_counts_kernel<<<(unsigned)w.tiles_upper, CT_THREADS, 0, st>>>(plan, w.a_start, pos_before, neg_before, (long long *)tps,
+    merge_counts_kernel<<<(unsigned)w.tiles_upper, MC_THREADS + 32, 0, st>>>(plan, w.a_start, pos_before, neg_before, (long long *)tps,
                                                                        (long long *)fps, w.status, w.counter, w.totals);
     MSS_CHECK_LAUNCH();
     return MSS_OK;
@@ -656,16 +889,21 @@ static int tail1_enqueue(const int64_t *tps_, const int64_t *fps_, const unsigne
     MSS_REQUIRE(w.tiles_upper < (1ull << 31), "tail: T too large");
     MSS_CHECK_CUDA(cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, st));
     if (w.tiles_upper == 0) return MSS_OK;
-    roc_compact_kernel<<<(unsigned)w.tiles_upper, CT_THREADS, 0, st>>>(tps, fps, d_T, T_host, recall_level, w.status, w.counter,
-                                                                      w.tile_best, w.tps_k, w.fps_k, w.totals);
+    // sub-tiles per tile: fat tiles for big inputs (one look-back per 16384 thresholds), >= ~4 tiles per SM for small ones
+    const long long T_upper = d_T ? (long long)w.tiles_upper * RC_SUBTILE : (long long)T_host;
+    const int sub = (int)std::max<long long>(1, std::min<long long>(RC_SUB, T_upper / ((long long)RC_SUBTILE * 4 * sm_count())));
+    const long long tile_thr = (long long)sub * RC_SUBTILE;
+    const unsigned tiles = (unsigned)((T_upper + tile_thr - 1) / tile_thr);
+    roc_compact_kernel<<<tiles, RC_THREADS + 32, 0, st>>>(tps, fps, d_T, T_host, sub, recall_level, w.status, w.counter,
+                                                          w.tile_best, w.tps_k, w.fps_k, w.totals);
     MSS_CHECK_LAUNCH();
     int n_partial = 0;
-    if (w.tiles_upper > 1024) {
-        fpr_reduce_kernel<<<256, CT_THREADS, 0, st>>>(w.tile_best, d_T, T_host, w.partial);
+    if (tiles > 1024) {
+        fpr_reduce_kernel<<<256, CT_THREADS, 0, st>>>(w.tile_best, d_T, T_host, tile_thr, w.partial);
         MSS_CHECK_LAUNCH();
         n_partial = 256;
     }
-    fpr_final_kernel<<<1, CT_THREADS, 0, st>>>(n_partial ? w.partial : w.tile_best, n_partial, fps, d_T, T_host, w.results);
+    fpr_final_kernel<<<1, CT_THREADS, 0, st>>>(n_partial ? w.partial : w.tile_best, n_partial, fps, d_T, T_host, tile_thr, w.results);
     MSS_CHECK_LAUNCH();
     return MSS_OK;
 }
@@ -719,7 +957,8 @@ static int tail2_run(const int64_t *tps_, const int64_t *fps_, int64_t T, int64_
     lj.roc = RocTerm{w.tps_k, w.fps_k, tps + (T - 1), fps + (T - 1)};
     leaf_bounds_kernel<<<dim3((unsigned)((max_leaves + 1 + 255) / 256), 2), 256, 0, st>>>(tt);
     MSS_CHECK_LAUNCH();
-    leaf_sum_kernel<<<dim3((unsigned)((max_leaves * 8 + 255) / 256), 2), 256, 0, st>>>(lj);
+    MSS_CHECK_CUDA(cudaFuncSetAttribute(leaf_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM));   // per device: set every time
+    leaf_sum_kernel<<<dim3((unsigned)((max_leaves + LS_LEAVES - 1) / LS_LEAVES), 2), LS_THREADS, LS_SMEM, st>>>(lj);
     MSS_CHECK_LAUNCH();
     subtree_combine_kernel<<<dim3((max_front + 127) / 128, 2), 128, 0, st>>>(cj);
     MSS_CHECK_LAUNCH();

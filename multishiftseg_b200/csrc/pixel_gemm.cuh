@@ -293,11 +293,22 @@ struct PixelGemmPlan {
     int slices, grid;
     long long n_items;
 };
-inline PixelGemmPlan pixel_gemm_plan(long long B, int tiles_per_image, int sms) {
+inline PixelGemmPlan pixel_gemm_plan(long long B, int tiles_per_image, int sms, bool shared_table = false) {
     PixelGemmPlan p;
     // B <= SMs: S = SMs / B slices per image, one work item per CTA; otherwise whole images, round-robin
     p.slices = (B <= sms) ? (tiles_per_image < sms / (int)B ? tiles_per_image : sms / (int)B) : 1;
     if (p.slices < 1) p.slices = 1;
+    if (shared_table && B <= sms) {
+        // One table for every image (the DeepLab head): items need not be image-aligned per CTA, so pick the slice count
+        // that makes B * S a multiple of the SM count -- every SM gets the same number of items (B = 8: S = 37, 2 items
+        // per CTA on all 148 SMs instead of 1 item on 144 of them).
+        long long a = B, b = sms;
+        while (b) { const long long t = a % b; a = b; b = t; }          // a = gcd(B, sms)
+        const int unit = (int)(sms / a);
+        const int want = (int)((sms + B - 1) / B);
+        const int s = (want + unit - 1) / unit * unit;
+        if (s <= tiles_per_image) p.slices = s;
+    }
     p.n_items = B * p.slices;
     p.grid = (int)(p.n_items < sms ? p.n_items : sms);
     return p;

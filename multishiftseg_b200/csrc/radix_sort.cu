@@ -248,37 +248,36 @@ radix_histogram_kernel(const SortPlan *__restrict__ plan, unsigned long long *__
         }
 }
 
-// hist[seg][pass][256] -> exclusive prefix (in place), one warp-scan per (segment, pass); a digit whose histogram
-// has a single non-empty bin leaves every key where it is: the pass is skipped for that segment (allow_skip).
+// hist[seg][pass][256] -> exclusive prefix (in place): warp w scans the histogram of (segment w / 4, pass w % 4), 8 bins
+// per lane.  A digit whose histogram has a single non-empty bin leaves every key where it is: the pass is skipped for
+// that segment (allow_skip).
 __global__ void __launch_bounds__(RADIX)
 radix_scan_bins_kernel(unsigned long long *__restrict__ hist, SortPlan *plan, int allow_skip) {
-    __shared__ unsigned long long s_warp[RADIX / 32];
-    __shared__ unsigned char s_skip[2][4];
-    for (int s = 0; s < 2; s++) {
-        const unsigned long long n = (unsigned long long)plan->seg[s].n;
-        for (int p = 0; p < 4; p++) {
-            unsigned long long *h = hist + (s * 4 + p) * RADIX;
-            unsigned long long v = h[threadIdx.x], inc = v;
-            const int single = __syncthreads_or(allow_skip && n > 0 && v == n);
+    __shared__ unsigned char s_skip[8];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long n = (unsigned long long)plan->seg[warp >> 2].n;
+    unsigned long long *h = hist + warp * RADIX + lane * 8;
+    unsigned long long v[8], sum = 0;
+    bool single = false;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
-                if ((threadIdx.x & 31) >= d) inc += t;
-            }
-            if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = inc;
-            __syncthreads();
-            unsigned long long base = 0;
-            for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += s_warp[w];
-            h[threadIdx.x] = base + inc - v;
-            if (threadIdx.x == 0) s_skip[s][p] = (unsigned char)(single || n == 0);
-            __syncthreads();
-        }
+    for (int j = 0; j < 8; j++) { v[j] = h[j]; sum += v[j]; single |= (v[j] == n); }
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
     }
+    unsigned long long run = inc - sum;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { h[j] = run; run += v[j]; }
+    const bool any_single = __any_sync(0xffffffffu, single);
+    if (lane == 0) s_skip[warp] = (unsigned char)((allow_skip && n > 0 && any_single) || n == 0);
+    __syncthreads();
     if (threadIdx.x < 2) {
         const int s = threadIdx.x;
         int cur = 0;                                         // 0: data in x, 1: data in y
         for (int p = 0; p < 4; p++) {
-            if (s_skip[s][p]) plan->sel[s][p] = 2;
+            if (s_skip[s * 4 + p]) plan->sel[s][p] = 2;
             else { plan->sel[s][p] = (unsigned char)cur; cur ^= 1; }
         }
         plan->copy_back[s] = (unsigned char)cur;
@@ -338,7 +337,7 @@ struct SweepSmem {
 // kernel spilled)
 // FULL: the tile holds exactly SORT_TILE keys (every tile but possibly the last): no bounds predicates.
 template <typename DigitFn, bool FULL, bool DIG>
-__device__ __forceinline__ void sweep_tile(SweepSmem<DIG> &sm, int sstride, int nd, DigitFn digit_of) {
+__device__ __forceinline__ void sweep_tile(SweepSmem<DIG> &sm, int sstride, int nd, DigitFn digit_of, int match_nbits = 8) {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // (tile context is re-read from shared memory where it is needed instead of being carried in registers)
     const int tile_n = FULL ? SORT_TILE : (int)(sm.n - (long long)sm.tile * SORT_TILE);
@@ -367,7 +366,19 @@ __device__ __forceinline__ void sweep_tile(SweepSmem<DIG> &sm, int sstride, int 
     unsigned peers[SORT_IPT];
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
-        if (FULL) peers[i] = match8_full(dig(i));
+        if (DIG) {
+            // destinations fit in digit_of.steps bits (8 GPUs: 3 ballots per key instead of 8)
+            const bool valid = FULL || wbase + i * 32 < tile_n;
+            const unsigned d = valid ? dig(i) : 0u;
+            unsigned pm = __ballot_sync(0xffffffffu, valid);
+            if (!valid) pm = ~pm;
+            for (int b = 0; b < match_nbits; b++) {
+                const bool bit = (d >> b) & 1u;
+                const unsigned mm = __ballot_sync(0xffffffffu, bit);
+                pm &= bit ? mm : ~mm;
+            }
+            peers[i] = pm;
+        } else if (FULL) peers[i] = match8_full(dig(i));
         else {
             const bool valid = wbase + i * 32 < tile_n;
             peers[i] = match_bits<8>(valid ? dig(i) : 0u, valid);
@@ -555,9 +566,9 @@ partition_scatter_kernel(const uint32_t *__restrict__ keys, long long n, const u
     __syncthreads();
     const SplitterDigit dg{sm.spl, nspl, steps};
     if ((long long)(sm.tile + 1) * SORT_TILE <= n)
-        sweep_tile<SplitterDigit, true, true>(sm, sstride, nd, dg);
+        sweep_tile<SplitterDigit, true, true>(sm, sstride, nd, dg, steps);
     else
-        sweep_tile<SplitterDigit, false, true>(sm, sstride, nd, dg);
+        sweep_tile<SplitterDigit, false, true>(sm, sstride, nd, dg, steps);
 }
 
 // top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536).
@@ -587,7 +598,9 @@ __device__ __forceinline__ void kh_add(unsigned *s_hist, unsigned b, bool valid)
 
 __global__ void __launch_bounds__(KH_THREADS, 1)
 keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift, unsigned nbins, int every,
-                      unsigned long long *__restrict__ hist) {
+                      unsigned long long *__restrict__ hist, int refine, unsigned prefix) {
+    // refine: second-level histogram -- only keys whose top 16 bits equal `prefix` are counted, by their LOW 16 bits
+    // (a splitter that has to fall inside a heavy coarse bin is placed with this resolution)
     extern __shared__ __align__(16) unsigned s_hist[];
     __shared__ unsigned s_outside;      // keys of this CTA's chunk that fell outside the current window
     // contiguous chunk of whole uint4 groups per CTA; the <= 3 + 3 unaligned head / tail keys go to CTA 0
@@ -610,11 +623,21 @@ keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift,
             const bool in = g < g1;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (in) v = __ldg(k4 + g * every);
-            const unsigned b0 = (v.x >> shift) - base, b1 = (v.y >> shift) - base, b2 = (v.z >> shift) - base,
-                           b3 = (v.w >> shift) - base;
-            // the lane's own four keys first: adjacent pixels usually share a bin
-            if (in) outside += (b0 >= (unsigned)KH_WINDOW) + (b1 >= (unsigned)KH_WINDOW) + (b2 >= (unsigned)KH_WINDOW) +
-                               (b3 >= (unsigned)KH_WINDOW);
+            unsigned b0, b1, b2, b3;
+            if (refine) {
+                // keys outside the prefix get a bin that is in no window and is not counted as "outside" either
+                const bool p0 = (v.x >> 16) == prefix, p1 = (v.y >> 16) == prefix, p2 = (v.z >> 16) == prefix,
+                           p3 = (v.w >> 16) == prefix;
+                b0 = p0 ? (v.x & 0xffffu) - base : 0xffffffffu; b1 = p1 ? (v.y & 0xffffu) - base : 0xffffffffu;
+                b2 = p2 ? (v.z & 0xffffu) - base : 0xffffffffu; b3 = p3 ? (v.w & 0xffffu) - base : 0xffffffffu;
+                if (in) outside += (p0 && b0 >= (unsigned)KH_WINDOW) + (p1 && b1 >= (unsigned)KH_WINDOW) +
+                                   (p2 && b2 >= (unsigned)KH_WINDOW) + (p3 && b3 >= (unsigned)KH_WINDOW);
+            } else {
+                b0 = (v.x >> shift) - base; b1 = (v.y >> shift) - base; b2 = (v.z >> shift) - base; b3 = (v.w >> shift) - base;
+                // the lane's own four keys first: adjacent pixels usually share a bin
+                if (in) outside += (b0 >= (unsigned)KH_WINDOW) + (b1 >= (unsigned)KH_WINDOW) + (b2 >= (unsigned)KH_WINDOW) +
+                                   (b3 >= (unsigned)KH_WINDOW);
+            }
             const bool same4 = b0 == b1 && b0 == b2 && b0 == b3;
             if (__all_sync(0xffffffffu, same4 || !in)) {
                 // every lane holds four equal bins: one aggregation round with weight 4
@@ -641,7 +664,9 @@ keys_histogram_kernel(const uint32_t *__restrict__ keys, long long n, int shift,
             for (long long i = 0; i < n; i++) {
                 if (i == head) i += groups_all << 2;
                 if (i >= n) break;
-                const unsigned b = (__ldg(keys + i) >> shift) - base;
+                const uint32_t kk = __ldg(keys + i);
+                if (refine && (kk >> 16) != prefix) continue;
+                const unsigned b = (refine ? (kk & 0xffffu) : (kk >> shift)) - base;
                 if (b < (unsigned)KH_WINDOW) atomicAdd(s_hist + b, 1u);
                 else outside++;
             }
@@ -774,7 +799,8 @@ extern "C" int mss_sort_keys(uint32_t *keys_a, int64_t n_a, uint32_t *keys_b, in
                         nullptr);
 }
 
-static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist, void *stream);
+static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist, void *stream, int refine = 0,
+                          unsigned prefix = 0);
 
 extern "C" int mss_keys_histogram(const uint32_t *keys, int64_t n, int bits, int64_t *hist, void *stream) {
     return keys_histogram(keys, n, bits, 1, hist, stream);
@@ -786,7 +812,14 @@ extern "C" int mss_keys_histogram_sampled(const uint32_t *keys, int64_t n, int b
     return keys_histogram(keys, n, bits, every, hist, stream);
 }
 
-static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist, void *stream) {
+extern "C" int mss_keys_histogram_refine(const uint32_t *keys, int64_t n, unsigned prefix16, int every, int64_t *hist,
+                                         void *stream) {
+    MSS_REQUIRE(every >= 1 && prefix16 <= 0xffffu, "mss_keys_histogram_refine: every >= 1 and prefix16 < 65536 required");
+    return keys_histogram(keys, n, 16, every, hist, stream, 1, prefix16);
+}
+
+static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, int64_t *hist, void *stream, int refine,
+                          unsigned prefix) {
     MSS_REQUIRE(bits >= 1 && bits <= 16 && hist, "mss_keys_histogram: bits must be 1..16");
     MSS_REQUIRE(n >= 0, "mss_keys_histogram: n < 0");
     cudaStream_t st = (cudaStream_t)stream;
@@ -796,7 +829,8 @@ static int keys_histogram(const uint32_t *keys, int64_t n, int bits, int every, 
     MSS_CHECK_CUDA(opt_in_smem());
     // one CTA per SM (128 KB window each); small inputs use fewer CTAs (>= 16 K keys per CTA)
     int grid = (int)std::max<long long>(1, std::min<long long>((n / every + 16383) / 16384, (long long)sm_count()));
-    keys_histogram_kernel<<<grid, KH_THREADS, KH_SMEM, st>>>(keys, n, 32 - bits, 1u << bits, every, (unsigned long long *)hist);
+    keys_histogram_kernel<<<grid, KH_THREADS, KH_SMEM, st>>>(keys, n, 32 - bits, 1u << bits, every, (unsigned long long *)hist,
+                                                            refine, prefix);
     MSS_CHECK_LAUNCH();
     return MSS_OK;
 }

@@ -210,7 +210,7 @@ def _streams(s, l):
 def test_counts_and_tail_stage_level(M, n, mode, p_ood):
     """merge-path counts over the two sorted streams == the integer spec (oracle.ood_counts), with and without the
     multi-GPU prefixes; the tail over them == the C oracle."""
-    s, l = gi.metric_case(11, n, mode, p_ood, 0.05, label_dtype="uint8")
+    s, l = gi.metric_case(11, n, mode, min(max(p_ood, 0.1), 0.9), 0.05, label_dtype="uint8")
     if p_ood == 0.0:
         l[l == 1] = 0
     if p_ood == 1.0:

@@ -29,6 +29,7 @@ for n in [int(a) for a in args] or [1<<21, 1<<23, 1<<25, 1<<27]:
     def cp():
         buf.keys.copy_(k0)
     t_s=ev(srt)-ev(cp)
+    srt(); torch.cuda.synchronize()      # leave the streams sorted for the stages below
     neg,pos=buf.streams(m,npos)
     t_c=ev(lambda: metric.counts_from_sorted(neg,m-npos,pos,npos))
     tps,fps=metric.counts_from_sorted(neg,m-npos,pos,npos)
