@@ -250,6 +250,18 @@ MSS_API int mss_partition_count(const uint32_t *keys, int64_t n, const uint32_t 
 MSS_API int mss_partition_scatter_keys(const uint32_t *keys, int64_t n, const uint32_t *splitters, int parts,
                                const uint64_t *dst_keys_host, const int64_t *dst_offsets_host,
                                void *workspace, size_t workspace_bytes, void *stream);
+/* The same two steps for BOTH streams of an evaluator in one call each (one host synchronisation per step; the splitters
+ * are a HOST array here).  n_neg / n_pos as read with mss_eval_state_host.
+ *   mss_eval_partition_count    out_counts_host[0 .. parts) = in-distribution keys per destination, [parts .. 2 parts) = OOD
+ *   mss_eval_partition_scatter  destination d's buffer dst_keys_host[d] receives this rank's in-distribution bucket at element
+ *                               offset dst_neg_offsets_host[d] and its OOD bucket at dst_pos_offsets_host[d]
+ * workspace: mss_eval_partition_workspace_bytes(n_neg, n_pos, parts). */
+MSS_API size_t mss_eval_partition_workspace_bytes(int64_t n_neg, int64_t n_pos, int parts);
+MSS_API int mss_eval_partition_count(const mss_eval_buffers *ev, int64_t n_neg, int64_t n_pos, const uint32_t *splitters_host,
+                             int parts, int64_t *out_counts_host, void *workspace, size_t workspace_bytes, void *stream);
+MSS_API int mss_eval_partition_scatter(const mss_eval_buffers *ev, int64_t n_neg, int64_t n_pos, const uint32_t *splitters_host,
+                               int parts, const uint64_t *dst_keys_host, const int64_t *dst_neg_offsets_host,
+                               const int64_t *dst_pos_offsets_host, void *workspace, size_t workspace_bytes, void *stream);
 /* two sorted key arrays (negatives = in-distribution, positives = OOD) -> per distinct key of their union the
  * cumulative counts  tps[k] = pos_before + #{positives with key <= key_k},  fps[k] = neg_before + #{negatives with
  * key <= key_k}  (int64; one merge-path pass).  tps/fps need room for n_neg + n_pos entries.  *T_host = number of

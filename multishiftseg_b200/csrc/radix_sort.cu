@@ -103,41 +103,54 @@ __global__ void sort_plan_kernel(SortPlan *plan, uint32_t *xa, uint32_t *ya, lon
 // Shared-memory atomics cost ~1-2 cycles per LANE on sm_100 and the digits of real score distributions are
 // extremely skewed (sign/exponent bits; zeroed mantissa bits of fp16-born scores), so contention-sensitive
 // schemes are out.  Every LANE owns private counters instead -- plain load / add / store, no atomics, no
-// dependence on the key distribution.  ncu (round 1, 32 M keys) on the first form of this idea, 4 warps per
-// SM with 32-bit counters and register-prefetched global loads: 814 us, issue 6.5 %, 4 of 64 warp slots --
-// pure latency.  This form:
-//   * 16-bit counters (16 KB per warp) -> 12 warps per SM: warp = (group g of 3, digit d of 4); the four
-//     digit-warps of a group count the same keys, the three groups split every chunk;
-//     counter (bin b, lane l) of a warp is the halfword at b*64 + 2*l;
-//   * keys arrive through a 4-stage ring of 6 KB bulk copies (cp.async.bulk + mbarrier, one elected lane),
-//     which keeps ~18 KB per SM in flight instead of 1.5 KB;
-//   * a lane adds at most 16 to one counter per chunk, so counters are folded into 32-bit per-CTA totals every
-//     HIST_EPOCH (<= 4095) chunks -- warp-local, no CTA barrier.
+// dependence on the key distribution.  History (ncu, B200):
+//   round 1, first form  4 warps per SM, 32-bit counters, register-prefetched global loads: 814 us per 32 M keys, issue
+//                        6.5 %, 4 of 64 warp slots -- pure latency;
+//   round 1, second form 16-bit counters (16 KB per warp) -> 12 warps per SM, keys through a 4-stage ring of bulk copies:
+//                        394 us per 134 M keys; 40 % of the stall samples on the shared-memory round trip of the
+//                        load-add-store chain (short scoreboard), issue 47 %;
+//   round 2, this form   8-BIT counters (8 KB per warp) -> 20 warps per SM to hide that round trip: warp = (group g of 5,
+//                        digit d of 4); the four digit-warps of a group count the same keys, the five groups split every
+//                        chunk; counter (bin b, lane l) of a warp is the byte at b*32 + l.  Measured: 448 us per 134 M
+//                        keys INCLUDING the zeroing of the passes' 268 MB of status words (side job below) -- the same as
+//                        the second form plus its separate memset; the kernel is bound by its ~52 instructions per key
+//                        (IMAD / shift address arithmetic of four digits), not by the round trip any more.
+//   * keys arrive through a 4-stage ring of 10 KB bulk copies (cp.async.bulk + mbarrier, one elected lane);
+//   * a lane adds at most 16 to one counter per chunk, so the bytes are folded into 32-bit per-CTA totals every
+//     HIST_EPOCH = 15 chunks (<= 240 per byte) -- warp-local, no CTA barrier; the fold sums a bin's 32 bytes with 8 dp4a.
 // Two keys are in flight per lane; when they hit the same counter both store the merged total.
 // blockIdx.y = segment of the plan; a segment uses as many of the gridDim.x CTAs as it has work for.
-constexpr int HIST_WARPS = 12;
-constexpr int HIST_THREADS = HIST_WARPS * 32;                  // 384
-constexpr int HIST_GROUPS = HIST_WARPS / 4;                    // 3
-constexpr int HIST_CHUNK_KEYS = HIST_GROUPS * 32 * 4 * 4;      // 1536 keys = 6 KB: 4 uint4 per lane per group
+constexpr int HIST_GROUPS = 5;
+constexpr int HIST_WARPS = HIST_GROUPS * 4;                    // 20
+constexpr int HIST_THREADS = HIST_WARPS * 32;                  // 640
+constexpr int HIST_CHUNK_KEYS = HIST_GROUPS * 32 * 4 * 4;      // 2560 keys = 10 KB: 4 uint4 per lane per group
 constexpr int HIST_CHUNK_BYTES = HIST_CHUNK_KEYS * 4;
 constexpr int HIST_STAGES = 4;
-constexpr int HIST_WARP_BYTES = RADIX * 32 * 2;                // 16 KB of u16 counters
-constexpr int HIST_EPOCH = 4000;
+constexpr int HIST_WARP_BYTES = RADIX * 32;                    // 8 KB of u8 counters
+constexpr int HIST_EPOCH = 15;
 constexpr int HIST_SMEM = HIST_WARPS * HIST_WARP_BYTES + HIST_STAGES * HIST_CHUNK_BYTES + 4 * RADIX * 4 +
                           2 * HIST_STAGES * 8 + 128;
 
-__device__ __forceinline__ unsigned lds_u16(uint32_t a) {
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+__device__ __forceinline__ unsigned lds_u8(uint32_t a) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
-__device__ __forceinline__ void sts_u16(uint32_t a, unsigned v) {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+__device__ __forceinline__ void sts_u8(uint32_t a, unsigned v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(HIST_THREADS, 1)
-radix_histogram_kernel(const SortPlan *__restrict__ plan, unsigned long long *__restrict__ hist_all, int epoch_chunks) {
+radix_histogram_kernel(const SortPlan *__restrict__ plan, unsigned long long *__restrict__ hist_all, int epoch_chunks,
+                       uint4 *__restrict__ zero_base, size_t zero_chunks) {
     extern __shared__ __align__(128) unsigned char s_raw[];
+    // Side job: zero the look-back status words of the four passes (2 KB per tile and pass: 268 MB for 134 M keys).
+    // This kernel is bound by its shared-memory counter updates, its store path is idle.
+    {
+        const size_t nthr = (size_t)gridDim.x * gridDim.y * HIST_THREADS;
+        for (size_t i = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * HIST_THREADS + threadIdx.x; i < zero_chunks; i += nthr)
+            zero_base[i] = make_uint4(0, 0, 0, 0);
+    }
     const SortSeg seg = plan->seg[blockIdx.y];
     const uint32_t *__restrict__ keys = seg.x;
     const long long n = seg.n;
@@ -146,8 +159,8 @@ radix_histogram_kernel(const SortPlan *__restrict__ plan, unsigned long long *__
     const unsigned grid = (unsigned)max(1ll, min((long long)gridDim.x, (n + 4 * HIST_CHUNK_KEYS - 1) / (4 * HIST_CHUNK_KEYS)));
     if (n == 0 || blockIdx.x >= grid) return;
 
-    unsigned char *s_cnt = s_raw;                                                  // [12][256][32] u16
-    uint4 *s_ring = reinterpret_cast<uint4 *>(s_raw + HIST_WARPS * HIST_WARP_BYTES);   // [4][384] uint4
+    unsigned char *s_cnt = s_raw;                                                  // [20][256][32] u8
+    uint4 *s_ring = reinterpret_cast<uint4 *>(s_raw + HIST_WARPS * HIST_WARP_BYTES);   // [4][640] uint4
     unsigned *s_tot = reinterpret_cast<unsigned *>(s_ring + HIST_STAGES * (HIST_CHUNK_KEYS / 4));   // [4][256]
     uint64_t *s_full = reinterpret_cast<uint64_t *>(s_tot + 4 * RADIX), *s_empty = s_full + HIST_STAGES;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -180,9 +193,9 @@ radix_histogram_kernel(const SortPlan *__restrict__ plan, unsigned long long *__
     if (tid == 0)
         for (long long j = 0; j < HIST_STAGES && j < my_chunks; j++) issue(j);
 
-    const uint32_t mine = smem_u32(s_cnt) + warp * HIST_WARP_BYTES + lane * 2;
+    const uint32_t mine = smem_u32(s_cnt) + warp * HIST_WARP_BYTES + lane;
     const int shift = 8 * (int)digit;
-    // fold this warp's 16-bit counters into the CTA totals of its digit and zero them (warp-local)
+    // fold this warp's 8-bit counters into the CTA totals of its digit and zero them (warp-local)
     auto fold = [&]() {
         __syncwarp();
         uint32_t *w32 = reinterpret_cast<uint32_t *>(s_cnt + warp * HIST_WARP_BYTES);
@@ -191,10 +204,9 @@ radix_histogram_kernel(const SortPlan *__restrict__ plan, unsigned long long *__
             const int bin = r * 32 + lane;
             unsigned acc = 0;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {                                         // rotated: 32 lanes, 32 banks
-                const int wi = bin * 16 + ((j + (lane >> 1)) & 15);
-                const uint32_t v = w32[wi];
-                acc += (v & 0xffffu) + (v >> 16);
+            for (int j = 0; j < 8; j++) {                                          // rotated: 32 lanes, 32 banks
+                const int wi = bin * 8 + ((j + (lane >> 2)) & 7);
+                acc = __dp4a(w32[wi], 0x01010101u, acc);
                 w32[wi] = 0;
             }
             if (acc) atomicAdd(&s_tot[digit * RADIX + bin], acc);
@@ -217,12 +229,12 @@ radix_histogram_kernel(const SortPlan *__restrict__ plan, unsigned long long *__
                 const uint32_t k[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int h = 0; h < 4; h += 2) {
-                    const uint32_t a0 = mine + (((k[h] >> shift) & 255u) << 6);
-                    const uint32_t a1 = mine + (((k[h + 1] >> shift) & 255u) << 6);
+                    const uint32_t a0 = mine + (((k[h] >> shift) & 255u) << 5);
+                    const uint32_t a1 = mine + (((k[h + 1] >> shift) & 255u) << 5);
                     const unsigned add = 1u + (a0 == a1);
-                    const unsigned c0 = lds_u16(a0), c1 = lds_u16(a1);
-                    sts_u16(a0, c0 + add);
-                    sts_u16(a1, c1 + add);
+                    const unsigned c0 = lds_u8(a0), c1 = lds_u8(a1);
+                    sts_u8(a0, c0 + add);
+                    sts_u8(a1, c1 + add);
                 }
             }
         }
@@ -537,6 +549,12 @@ onesweep_pass_kernel(const SortPlan *__restrict__ plan, int pass, const unsigned
         sweep_tile<ShiftDigit, false, false>(sm, RADIX, RADIX, dg);
 }
 
+// (Round-2 experiment, not kept: a PERSISTENT form of this kernel -- 4 resident CTAs per SM walking tickets, the next
+// tile's keys loaded into the key registers right after the shared-memory scatter so that they arrive during the
+// look-back and the write-out -- was no faster: 44.2 vs 44.7 Gkeys/s at 134 M keys, 32.2 vs 35.0 at 8 M.  With four
+// independent CTAs per SM the hardware already overlaps one tile's load latency with the others' arithmetic; the pass is
+// bound by its ~84 instructions per key (ALU pipe 58 %, issue 53 %), not by exposed memory latency.)
+
 // a segment whose last executed pass wrote into the alternate buffer is copied back (odd number of live passes)
 __global__ void __launch_bounds__(256)
 sort_copy_back_kernel(const SortPlan *__restrict__ plan) {
@@ -569,6 +587,171 @@ partition_scatter_kernel(const uint32_t *__restrict__ keys, long long n, const u
         sweep_tile<SplitterDigit, true, true>(sm, sstride, nd, dg, steps);
     else
         sweep_tile<SplitterDigit, false, true>(sm, sstride, nd, dg, steps);
+}
+
+// The same exchange step for <= PB_MAX_PARTS destinations (one per GPU of a box) with BULK stores: after the tile has
+// been ordered by destination in shared memory, each destination's run (~4096 / parts keys) leaves the SM as ONE
+// cp.async.bulk shared -> global copy (TMA engine; 16-byte granules) instead of ~parts x 16 warp-wide 4-byte store
+// instructions -- over NVLink that means few large writes per tile instead of thousands of 128-byte ones.  A bulk copy
+// needs source and destination 16-byte aligned, so the look-back runs BEFORE the shared-memory scatter here (it tells
+// where in the destination buffer the run starts) and every run is placed in shared memory at an offset congruent to its
+// destination address modulo 16 bytes; the <= 3 keys before the first and after the last 16-byte granule are stored
+// individually.  Ranking (ballot matching on the few destination bits) is the tile routine's.
+constexpr int PB_MAX_PARTS = 32;
+constexpr int PB_KEYS = SORT_TILE + 8 * PB_MAX_PARTS;          // room for the alignment gaps between runs (<= 6 keys each)
+
+struct PartSmem {
+    __align__(16) uint32_t keys[PB_KEYS];
+    unsigned warp_hist[SORT_WARPS][PB_MAX_PARTS];     // per-warp destination counts -> scatter bases
+    unsigned long long dst[PB_MAX_PARTS];             // byte address of this tile's run in destination d
+    unsigned start[PB_MAX_PARTS], count[PB_MAX_PARTS];
+    uint32_t spl[PB_MAX_PARTS];
+    unsigned tile;
+};
+
+__device__ __forceinline__ void bulk_store_1d(unsigned long long gdst, uint32_t smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+
+template <bool FULL>
+__device__ __forceinline__ void partition_tile_bulk(PartSmem &sm, const uint32_t *__restrict__ keys_in, long long n,
+                                                    const unsigned long long *__restrict__ table,
+                                                    unsigned long long *status, int sstride, int nd, int steps) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned tile = sm.tile;
+    const int tile_n = FULL ? SORT_TILE : (int)(n - (long long)tile * SORT_TILE);
+    const SplitterDigit digit_of{sm.spl, nd - 1, steps};
+
+    uint32_t key[SORT_IPT];
+    const int wbase = warp * (32 * SORT_IPT) + lane;
+    const uint32_t *kp = keys_in + (long long)tile * SORT_TILE + wbase;
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) key[i] = (FULL || wbase + i * 32 < tile_n) ? __ldg(kp + i * 32) : 0u;
+    unsigned dpk[SORT_IPT / 4];
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        const unsigned d = digit_of(key[i]);
+        dpk[i >> 2] = (i & 3) ? (dpk[i >> 2] | (d << (8 * (i & 3)))) : d;
+    }
+    auto dig = [&](int i) -> unsigned { return (dpk[i >> 2] >> (8 * (i & 3))) & 255u; };
+
+    // rank inside the warp (stable): ballots on the destination bits, running per-destination counters
+    unsigned rank2[SORT_IPT / 2];
+    const unsigned lt = lanemask_lt();
+    unsigned *wh = sm.warp_hist[warp];
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        const bool valid = FULL || wbase + i * 32 < tile_n;
+        const unsigned d = valid ? dig(i) : 0u;
+        unsigned pm = __ballot_sync(0xffffffffu, valid);
+        if (!valid) pm = ~pm;
+        for (int b = 0; b < steps; b++) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned mm = __ballot_sync(0xffffffffu, bit);
+            pm &= bit ? mm : ~mm;
+        }
+        const unsigned below = __popc(pm & lt);
+        unsigned old = 0;
+        if (below == 0 && valid) {
+            old = wh[d];
+            wh[d] = old + __popc(pm);
+        }
+        old = __shfl_sync(0xffffffffu, old, __ffs(pm) - 1);
+        const unsigned r16 = old + below;
+        rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r16 << 16)) : r16;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d < nd: tile count, publish, look back, destination address of this tile's run
+    if ((int)tid < nd) {
+        const unsigned d = tid;
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) tot += sm.warp_hist[w][d];
+        unsigned long long *my = status + (size_t)tile * sstride + d;
+        st_status(my, (tile == 0 ? FLAG_INC : FLAG_AGG) | tot);
+        unsigned long long prefix = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            const unsigned long long *p = my - sstride;
+            for (;;) {
+                unsigned long long stt[LB_WINDOW];
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++) stt[j] = (j <= t) ? ld_status(p - (size_t)j * sstride) : FLAG_INC;
+                unsigned lowest = 0xffffffffu;
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++) lowest = min(lowest, (unsigned)(stt[j] >> 32));
+                if (lowest < 0x40000000u) continue;                 // some predecessor has not even counted yet: read again
+                bool done = false;
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++) {
+                    if (!done) prefix += stt[j] & VAL_MASK;
+                    done = done || (unsigned)(stt[j] >> 32) >= 0x80000000u;
+                }
+                if (done) break;
+                t -= LB_WINDOW;
+                p -= (size_t)LB_WINDOW * sstride;
+            }
+            st_status(my, FLAG_INC | (prefix + tot));
+        }
+        sm.dst[d] = __ldg(table + d) + 4ull * prefix;
+        sm.count[d] = tot;
+    }
+    __syncthreads();
+    // shared-memory layout: run d starts at a 4-key boundary plus (destination address / 4) mod 4
+    if (tid == 0) {
+        unsigned cur = 0;
+        for (int d = 0; d < nd; d++) {
+            const unsigned st0 = ((cur + 3u) & ~3u) + (unsigned)((sm.dst[d] >> 2) & 3ull);
+            sm.start[d] = st0;
+            cur = st0 + sm.count[d];
+        }
+    }
+    __syncthreads();
+    if ((int)tid < nd) {                                   // scatter base of (warp w, destination d)
+        unsigned run = sm.start[tid];
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) { const unsigned c = sm.warp_hist[w][tid]; sm.warp_hist[w][tid] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        if (FULL || wbase + i * 32 < tile_n) {
+            const unsigned r16 = (i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
+            sm.keys[wh[dig(i)] + r16] = key[i];
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the bulk-copy engine
+    __syncthreads();
+    // one thread per destination: <= 3 head keys, one bulk copy, <= 3 tail keys
+    if ((int)tid < nd) {
+        const unsigned cnt = sm.count[tid], st0 = sm.start[tid];
+        const unsigned long long a = sm.dst[tid];
+        const unsigned head = min(cnt, (unsigned)(((16ull - (a & 15ull)) & 15ull) >> 2));
+        const unsigned body = (cnt - head) & ~3u;
+        for (unsigned j = 0; j < head; j++) *reinterpret_cast<uint32_t *>(a + 4ull * j) = sm.keys[st0 + j];
+        if (body) bulk_store_1d(a + 4ull * head, smem_u32(&sm.keys[st0 + head]), body * 4u);
+        for (unsigned j = head + body; j < cnt; j++) *reinterpret_cast<uint32_t *>(a + 4ull * j) = sm.keys[st0 + j];
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // shared memory must outlive the copy's reads
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS, 4)
+partition_scatter_bulk_kernel(const uint32_t *__restrict__ keys, long long n, const uint32_t *__restrict__ splitters, int nspl,
+                              int steps, const unsigned long long *__restrict__ table, unsigned long long *tile_status,
+                              int sstride, unsigned *tile_counter) {
+    __shared__ PartSmem sm;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) sm.tile = atomicAdd(tile_counter, 1u);
+    if (tid < SORT_WARPS * PB_MAX_PARTS) (&sm.warp_hist[0][0])[tid] = 0;
+    if ((int)tid < nspl) sm.spl[tid] = __ldg(splitters + tid);
+    __syncthreads();
+    if ((long long)(sm.tile + 1) * SORT_TILE <= n)
+        partition_tile_bulk<true>(sm, keys, n, table, tile_status, sstride, nspl + 1, steps);
+    else
+        partition_tile_bulk<false>(sm, keys, n, table, tile_status, sstride, nspl + 1, steps);
 }
 
 // top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536).
@@ -747,7 +930,9 @@ int sort_enqueue(const mss_eval_buffers *ev, uint32_t *xa, int64_t na, uint32_t 
         return MSS_ERR_WORKSPACE;
     }
     MSS_REQUIRE(w.tiles_upper < (1ull << 31), "sort: n too large");
-    MSS_CHECK_CUDA(cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, st));
+    // histograms + tile counters by a small memset; the (large) status arrays are zeroed by the histogram kernel
+    const size_t small_zero = (size_t)((char *)w.status - w.zero_base);
+    MSS_CHECK_CUDA(cudaMemsetAsync(w.zero_base, 0, n_upper > 0 ? small_zero : w.zero_bytes, st));
     if (ev)
         sort_plan_kernel<<<1, 1, 0, st>>>(w.plan, nullptr, nullptr, 0, nullptr, nullptr, 0, (const EvalState *)ev->state,
                                           ev->keys, w.alt, ev->capacity);
@@ -761,7 +946,8 @@ int sort_enqueue(const mss_eval_buffers *ev, uint32_t *xa, int64_t na, uint32_t 
     // one CTA per SM and segment (192 KB of private counters each); a segment uses only the CTAs it has chunks for
     const int hgrid = (int)std::max<long long>(1, std::min<long long>((n_upper + 4 * HIST_CHUNK_KEYS - 1) / (4 * HIST_CHUNK_KEYS),
                                                                       (long long)sm_count()));
-    radix_histogram_kernel<<<dim3(hgrid, 2), HIST_THREADS, HIST_SMEM, st>>>(w.plan, w.hist, hist_epoch_chunks());
+    radix_histogram_kernel<<<dim3(hgrid, 2), HIST_THREADS, HIST_SMEM, st>>>(w.plan, w.hist, hist_epoch_chunks(), (uint4 *)w.status,
+                                                                            (w.zero_bytes - small_zero) / 16);
     MSS_CHECK_LAUNCH();
     radix_scan_bins_kernel<<<1, RADIX, 0, st>>>(w.hist, w.plan, sort_allow_skip());
     MSS_CHECK_LAUNCH();
@@ -942,8 +1128,13 @@ static int scatter_to(const uint32_t *keys, int64_t n, const uint32_t *splitters
     MSS_REQUIRE(tiles < (1ull << 31), "%s: n too large", who);
     MSS_CHECK_CUDA(cudaMemsetAsync(counter, 0, (size_t)((char *)(status + tiles * sstride) - (char *)counter), st));
     MSS_CHECK_CUDA(cudaMemcpyAsync(table, table_host, (size_t)parts * 8, cudaMemcpyHostToDevice, st));
-    partition_scatter_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(keys, n, splitters, parts - 1, splitter_steps(parts),
-                                                                      table, status, sstride, counter);
+    static const bool no_bulk = [] { const char *e = getenv("MSS_PARTITION_NO_BULK"); return e && atoi(e); }();   // A/B switch
+    if (parts <= PB_MAX_PARTS && !no_bulk)
+        partition_scatter_bulk_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(keys, n, splitters, parts - 1, splitter_steps(parts),
+                                                                               table, status, sstride, counter);
+    else
+        partition_scatter_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(keys, n, splitters, parts - 1, splitter_steps(parts),
+                                                                          table, status, sstride, counter);
     MSS_CHECK_LAUNCH();
     return MSS_OK;
 }
@@ -990,5 +1181,81 @@ extern "C" int mss_partition_keys(const uint32_t *keys, int64_t n, const uint32_
     rc = scatter_to(keys, n, splitters, parts, h, workspace, front, st, "mss_partition_keys");
     if (rc) return rc;
     MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    return MSS_OK;
+}
+
+// ---- both streams of an evaluator per call (one host synchronisation instead of two per exchange step) -------------
+static bool eval_streams(const mss_eval_buffers *ev, int64_t n_neg, int64_t n_pos, const uint32_t **neg, const uint32_t **pos) {
+    if (!ev || !ev->keys || n_neg < 0 || n_pos < 0 || n_neg + n_pos > ev->capacity) return false;
+    *neg = ev->keys;
+    *pos = ev->keys + (ev->capacity - n_pos);
+    return true;
+}
+
+extern "C" size_t mss_eval_partition_workspace_bytes(int64_t n_neg, int64_t n_pos, int parts) {
+    return 4096 + 2 * RADIX * 8 + align_up(mss_partition_workspace_bytes(n_neg, parts), 256) +
+           align_up(mss_partition_workspace_bytes(n_pos, parts), 256);
+}
+
+extern "C" int mss_eval_partition_count(const mss_eval_buffers *ev, int64_t n_neg, int64_t n_pos, const uint32_t *splitters_host,
+                                        int parts, int64_t *out_counts_host, void *workspace, size_t workspace_bytes,
+                                        void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= RADIX && out_counts_host && workspace, "mss_eval_partition_count: bad arguments");
+    MSS_REQUIRE(parts == 1 || splitters_host, "mss_eval_partition_count: null splitters");
+    const uint32_t *neg, *pos;
+    MSS_REQUIRE(eval_streams(ev, n_neg, n_pos, &neg, &pos), "mss_eval_partition_count: bad evaluator / stream sizes");
+    MSS_REQUIRE(workspace_bytes >= 4096 + 2 * RADIX * 8, "mss_eval_partition_count: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *spl = (uint32_t *)workspace;                                      // [256]
+    unsigned long long *counts = (unsigned long long *)((char *)workspace + 4096);   // [2][256]
+    if (parts > 1) MSS_CHECK_CUDA(cudaMemcpyAsync(spl, splitters_host, (size_t)(parts - 1) * 4, cudaMemcpyHostToDevice, st));
+    MSS_CHECK_CUDA(cudaMemsetAsync(counts, 0, 2 * RADIX * 8, st));
+    int rc = MSS_OK;
+    if (n_neg) rc = count_into(neg, n_neg, spl, parts, counts, st);
+    if (rc == MSS_OK && n_pos) rc = count_into(pos, n_pos, spl, parts, counts + RADIX, st);
+    if (rc) return rc;
+    unsigned long long h[2 * RADIX];
+    MSS_CHECK_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, st));
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < parts; j++) {
+        out_counts_host[j] = (int64_t)h[j];
+        out_counts_host[parts + j] = (int64_t)h[RADIX + j];
+    }
+    return MSS_OK;
+}
+
+extern "C" int mss_eval_partition_scatter(const mss_eval_buffers *ev, int64_t n_neg, int64_t n_pos,
+                                          const uint32_t *splitters_host, int parts, const uint64_t *dst_keys_host,
+                                          const int64_t *dst_neg_offsets_host, const int64_t *dst_pos_offsets_host,
+                                          void *workspace, size_t workspace_bytes, void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= RADIX && dst_keys_host && dst_neg_offsets_host && dst_pos_offsets_host && workspace,
+                "mss_eval_partition_scatter: bad arguments");
+    MSS_REQUIRE(parts == 1 || splitters_host, "mss_eval_partition_scatter: null splitters");
+    const uint32_t *neg, *pos;
+    MSS_REQUIRE(eval_streams(ev, n_neg, n_pos, &neg, &pos), "mss_eval_partition_scatter: bad evaluator / stream sizes");
+    if (workspace_bytes < mss_eval_partition_workspace_bytes(n_neg, n_pos, parts)) {
+        set_error("mss_eval_partition_scatter: workspace too small (%zu < %zu)", workspace_bytes,
+                  mss_eval_partition_workspace_bytes(n_neg, n_pos, parts));
+        return MSS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *spl = (uint32_t *)workspace;
+    if (parts > 1) MSS_CHECK_CUDA(cudaMemcpyAsync(spl, splitters_host, (size_t)(parts - 1) * 4, cudaMemcpyHostToDevice, st));
+    unsigned long long hn[RADIX], hp[RADIX];
+    for (int j = 0; j < parts; j++) {
+        MSS_REQUIRE(dst_keys_host[j] && (dst_keys_host[j] & 3) == 0 && dst_neg_offsets_host[j] >= 0 && dst_pos_offsets_host[j] >= 0,
+                    "mss_eval_partition_scatter: bad destination %d", j);
+        hn[j] = (unsigned long long)dst_keys_host[j] + 4ull * (unsigned long long)dst_neg_offsets_host[j];
+        hp[j] = (unsigned long long)dst_keys_host[j] + 4ull * (unsigned long long)dst_pos_offsets_host[j];
+    }
+    char *w0 = (char *)workspace + 4096 + 2 * RADIX * 8;
+    const size_t b0 = align_up(mss_partition_workspace_bytes(n_neg, parts), 256);
+    int rc = MSS_OK;
+    if (n_neg) rc = scatter_to(neg, n_neg, spl, parts, hn, w0, b0, st, "mss_eval_partition_scatter");
+    if (rc == MSS_OK && n_pos)
+        rc = scatter_to(pos, n_pos, spl, parts, hp, w0 + b0, align_up(mss_partition_workspace_bytes(n_pos, parts), 256), st,
+                        "mss_eval_partition_scatter");
+    if (rc) return rc;
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));     // the host staging arrays must outlive the async copies
     return MSS_OK;
 }

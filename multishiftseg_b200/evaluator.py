@@ -122,6 +122,35 @@ class CudaBackend:
             L.check(lib.mss_partition_scatter_keys(keys.data_ptr(), m, spl.data_ptr(), parts, dk, do, ws.data_ptr(), nbytes,
                                                    L.stream_ptr(self.device)), "mss_partition_scatter_keys")
 
+    # -- both streams of a buffer per call (one host synchronisation per exchange step)
+    def partition_count2(self, buf, n_neg: int, n_pos: int, splitters: Sequence[int], parts: int):
+        """-> (negatives per destination, positives per destination)."""
+        import ctypes as C
+        lib = L.load()
+        spl = (C.c_uint32 * max(parts - 1, 1))(*[int(x) for x in splitters])
+        counts = (C.c_int64 * (2 * parts))()
+        ws = L.workspace(16384, self.device)
+        with torch.cuda.device(self.device):
+            L.check(lib.mss_eval_partition_count(C.byref(buf.c), n_neg, n_pos, spl, parts, counts, ws.data_ptr(), 16384,
+                                                 L.stream_ptr(self.device)), "mss_eval_partition_count")
+        return [int(c) for c in counts[:parts]], [int(c) for c in counts[parts:]]
+
+    def partition_scatter2(self, buf, n_neg: int, n_pos: int, splitters: Sequence[int], parts: int,
+                           dst_keys: Sequence[int], off_neg: Sequence[int], off_pos: Sequence[int]):
+        """Fused partition + exchange of both streams: destination d's buffer receives this rank's in-distribution bucket
+        at element offset ``off_neg[d]`` and its OOD bucket at ``off_pos[d]`` (peer memory for d != this rank)."""
+        import ctypes as C
+        lib = L.load()
+        spl = (C.c_uint32 * max(parts - 1, 1))(*[int(x) for x in splitters])
+        dk = (C.c_uint64 * parts)(*[int(x) for x in dst_keys])
+        on = (C.c_int64 * parts)(*[int(x) for x in off_neg])
+        op = (C.c_int64 * parts)(*[int(x) for x in off_pos])
+        nbytes = lib.mss_eval_partition_workspace_bytes(n_neg, n_pos, parts)
+        ws = L.workspace(nbytes, self.device)
+        with torch.cuda.device(self.device):
+            L.check(lib.mss_eval_partition_scatter(C.byref(buf.c), n_neg, n_pos, spl, parts, dk, on, op, ws.data_ptr(), nbytes,
+                                                   L.stream_ptr(self.device)), "mss_eval_partition_scatter")
+
     # -- peer-mapped receive buffers (torch symmetric memory: every rank can store into every rank's buffer)
     def peer_alloc(self, capacity: int):
         """Local half (may raise, e.g. out of memory): the symmetric allocation, not yet mapped by the peers."""
@@ -299,7 +328,7 @@ class StreamingEvaluator:
             exchange = "p2p" if hasattr(be, "peer_alloc") and not getattr(self, "_p2p_failed", False) else "nccl"
         send = None
         if exchange == "p2p":
-            send = [be.partition_count(neg, n_neg, splitters, world), be.partition_count(pos, n_pos, splitters, world)]
+            send = list(be.partition_count2(self.buf, n_neg, n_pos, splitters, world))
         else:
             pk_neg, c_neg = be.partition(neg, n_neg, splitters, world)
             pk_pos, c_pos = be.partition(pos, n_pos, splitters, world)
@@ -332,8 +361,7 @@ class StreamingEvaluator:
             off_neg = [int(all_counts[:rank, 0, d].sum()) for d in range(world)]
             off_pos = [cap - int(per_dst[1][d]) + int(all_counts[:rank, 1, d].sum()) for d in range(world)]
             dist.barrier(group=g)                                         # peers are done with the previous contents
-            be.partition_scatter(neg, n_neg, splitters, world, pb["key_ptrs"], off_neg)
-            be.partition_scatter(pos, n_pos, splitters, world, pb["key_ptrs"], off_pos)
+            be.partition_scatter2(self.buf, n_neg, n_pos, splitters, world, pb["key_ptrs"], off_neg, off_pos)
             dist.barrier(group=g)                                         # every rank's stores have landed
             rk = pb["keys"]
             r_neg, r_pos = rk[:m2_neg], rk[cap - m2_pos: cap]

@@ -171,8 +171,8 @@ def test_sort_single_bin_pass_skip(M, mode):
 
 
 def test_sort_histogram_counter_fold():
-    """The upfront digit histogram keeps 16-bit lane-private counters and folds them every HIST_EPOCH chunks;
-    MSS_HIST_EPOCH=2 (read once per process) makes a 5 M-key input cross many folds.  Unaligned key pointer too.
+    """The upfront digit histogram keeps 8-bit lane-private counters and folds them every HIST_EPOCH (<= 15) chunks;
+    MSS_HIST_EPOCH=2 (read once per process) makes a 5 M-key input cross many more folds.  Unaligned key pointer too.
     MSS_SORT_NOSKIP=1: the same process also checks the sort with the pass skip disabled."""
     import subprocess
     import sys
