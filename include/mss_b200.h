@@ -262,6 +262,18 @@ MSS_API int mss_eval_partition_count(const mss_eval_buffers *ev, int64_t n_neg, 
 MSS_API int mss_eval_partition_scatter(const mss_eval_buffers *ev, int64_t n_neg, int64_t n_pos, const uint32_t *splitters_host,
                                int parts, const uint64_t *dst_keys_host, const int64_t *dst_neg_offsets_host,
                                const int64_t *dst_pos_offsets_host, void *workspace, size_t workspace_bytes, void *stream);
+/* Exchange by REMOTE APPEND (the default multi-GPU path): the receive side is itself an evaluator buffer in peer-mapped
+ * memory.  Every key of this rank's evaluator is appended to the evaluator of the rank that owns its key range: a tile
+ * orders its keys by destination in shared memory, reserves its run with one system-scope atomicAdd on the destination's
+ * stream counter (over NVLink) and stores it with one bulk copy.  No counting pass, no all-gather of bucket sizes, no
+ * look-back, both streams in one launch.
+ *   dst_keys_host[d], dst_state_host[d]  device addresses of rank d's key buffer / MSS_EVAL_STATE_BYTES state
+ *   dst_capacity                         keys per destination buffer
+ * The caller zeroes the destination states, orders the call between two barriers, and every rank then reads its own state
+ * with mss_eval_state_host (which reports an overflow).  parts <= 32; workspace >= 4096 bytes.  Synchronises the stream. */
+MSS_API int mss_eval_exchange_append(const mss_eval_buffers *ev, int64_t n_neg, int64_t n_pos, const uint32_t *splitters_host,
+                             int parts, const uint64_t *dst_keys_host, const uint64_t *dst_state_host,
+                             int64_t dst_capacity, void *workspace, size_t workspace_bytes, void *stream);
 /* two sorted key arrays (negatives = in-distribution, positives = OOD) -> per distinct key of their union the
  * cumulative counts  tps[k] = pos_before + #{positives with key <= key_k},  fps[k] = neg_before + #{negatives with
  * key <= key_k}  (int64; one merge-path pass).  tps/fps need room for n_neg + n_pos entries.  *T_host = number of

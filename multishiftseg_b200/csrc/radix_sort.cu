@@ -754,6 +754,146 @@ partition_scatter_bulk_kernel(const uint32_t *__restrict__ keys, long long n, co
         partition_tile_bulk<false>(sm, keys, n, table, tile_status, sstride, nspl + 1, steps);
 }
 
+// ---- exchange by remote append ------------------------------------------------------------------------------
+// The receive side of the exchange is itself an evaluator buffer (two key streams + state) in peer-mapped memory.  A tile
+// orders its keys by destination in shared memory, RESERVES its run in every destination with one system-scope
+// atomicAdd on that destination's stream counter (over NVLink for a peer), and stores the run with one bulk copy.
+// Nothing has to be known in advance: no counting pass, no all-gather of bucket sizes, no look-back between tiles, and
+// both streams go in one launch.  The order inside a destination stream is the order of the reservations, which is fine:
+// a stream is a multiset.  Overflow: each stream is kept inside the destination buffer here; the two streams meeting in
+// the middle is detected by the owner when it reads its state (as for local appends).
+struct ExchangeDst {
+    unsigned long long keys[PB_MAX_PARTS];     // byte address of destination d's key buffer
+    unsigned long long state[PB_MAX_PARTS];    // byte address of destination d's EvalState
+    long long capacity;                        // keys per destination buffer
+};
+
+template <bool FULL>
+__device__ __forceinline__ void exchange_tile(PartSmem &sm, const uint32_t *__restrict__ keys_in, long long n, unsigned tile,
+                                              bool positives, const ExchangeDst &dst, int nd, int steps) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_n = FULL ? SORT_TILE : (int)(n - (long long)tile * SORT_TILE);
+    const SplitterDigit digit_of{sm.spl, nd - 1, steps};
+
+    uint32_t key[SORT_IPT];
+    const int wbase = warp * (32 * SORT_IPT) + lane;
+    const uint32_t *kp = keys_in + (long long)tile * SORT_TILE + wbase;
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) key[i] = (FULL || wbase + i * 32 < tile_n) ? __ldg(kp + i * 32) : 0u;
+    unsigned dpk[SORT_IPT / 4];
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        const unsigned d = digit_of(key[i]);
+        dpk[i >> 2] = (i & 3) ? (dpk[i >> 2] | (d << (8 * (i & 3)))) : d;
+    }
+    auto dig = [&](int i) -> unsigned { return (dpk[i >> 2] >> (8 * (i & 3))) & 255u; };
+
+    unsigned rank2[SORT_IPT / 2];
+    const unsigned lt = lanemask_lt();
+    unsigned *wh = sm.warp_hist[warp];
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        const bool valid = FULL || wbase + i * 32 < tile_n;
+        const unsigned d = valid ? dig(i) : 0u;
+        unsigned pm = __ballot_sync(0xffffffffu, valid);
+        if (!valid) pm = ~pm;
+        for (int b = 0; b < steps; b++) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned mm = __ballot_sync(0xffffffffu, bit);
+            pm &= bit ? mm : ~mm;
+        }
+        const unsigned below = __popc(pm & lt);
+        unsigned old = 0;
+        if (below == 0 && valid) {
+            old = wh[d];
+            wh[d] = old + __popc(pm);
+        }
+        old = __shfl_sync(0xffffffffu, old, __ffs(pm) - 1);
+        const unsigned r16 = old + below;
+        rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r16 << 16)) : r16;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d < nd: reserve this tile's run in destination d (one remote atomic), address of the run
+    if ((int)tid < nd) {
+        const unsigned d = tid;
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) tot += sm.warp_hist[w][d];
+        unsigned long long addr = 0;
+        if (tot) {
+            EvalState *es = reinterpret_cast<EvalState *>(dst.state[d]);
+            const unsigned long long base = atomicAdd_system(positives ? &es->n_pos : &es->n_neg, (unsigned long long)tot);
+            if (base + tot > (unsigned long long)dst.capacity) {
+                atomicAdd_system(&es->overflow, (unsigned long long)tot);      // dropped: the owner reports MSS_ERR_WORKSPACE
+                tot = 0;
+            } else {
+                // negatives fill the buffer upwards, positives downwards (the run itself is stored in ascending order)
+                addr = dst.keys[d] + 4ull * (positives ? (unsigned long long)dst.capacity - base - tot : base);
+            }
+        }
+        sm.dst[d] = addr;
+        sm.count[d] = tot;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned cur = 0;
+        for (int d = 0; d < nd; d++) {
+            unsigned c = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; w++) c += sm.warp_hist[w][d];       // (a dropped run still needs its shared-memory room)
+            const unsigned st0 = ((cur + 3u) & ~3u) + (unsigned)((sm.dst[d] >> 2) & 3ull);
+            sm.start[d] = st0;
+            cur = st0 + c;
+        }
+    }
+    __syncthreads();
+    if ((int)tid < nd) {
+        unsigned run = sm.start[tid];
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) { const unsigned c = sm.warp_hist[w][tid]; sm.warp_hist[w][tid] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_IPT; i++) {
+        if (FULL || wbase + i * 32 < tile_n) {
+            const unsigned r16 = (i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
+            sm.keys[wh[dig(i)] + r16] = key[i];
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if ((int)tid < nd) {
+        const unsigned cnt = sm.count[tid], st0 = sm.start[tid];
+        const unsigned long long a = sm.dst[tid];
+        const unsigned head = min(cnt, (unsigned)(((16ull - (a & 15ull)) & 15ull) >> 2));
+        const unsigned body = (cnt - head) & ~3u;
+        for (unsigned j = 0; j < head; j++) *reinterpret_cast<uint32_t *>(a + 4ull * j) = sm.keys[st0 + j];
+        if (body) bulk_store_1d(a + 4ull * head, smem_u32(&sm.keys[st0 + head]), body * 4u);
+        for (unsigned j = head + body; j < cnt; j++) *reinterpret_cast<uint32_t *>(a + 4ull * j) = sm.keys[st0 + j];
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// blockIdx.x < tiles_neg: a tile of the in-distribution stream, else of the OOD stream
+__global__ void __launch_bounds__(SORT_THREADS, 4)
+exchange_append_kernel(const uint32_t *__restrict__ neg, long long n_neg, const uint32_t *__restrict__ pos, long long n_pos,
+                       unsigned tiles_neg, const uint32_t *__restrict__ splitters, int nspl, int steps, ExchangeDst dst) {
+    __shared__ PartSmem sm;
+    const unsigned tid = threadIdx.x;
+    if (tid < SORT_WARPS * PB_MAX_PARTS) (&sm.warp_hist[0][0])[tid] = 0;
+    if ((int)tid < nspl) sm.spl[tid] = __ldg(splitters + tid);
+    __syncthreads();
+    const bool positives = blockIdx.x >= tiles_neg;
+    const unsigned tile = positives ? blockIdx.x - tiles_neg : blockIdx.x;
+    const uint32_t *keys = positives ? pos : neg;
+    const long long n = positives ? n_pos : n_neg;
+    if ((long long)(tile + 1) * SORT_TILE <= n) exchange_tile<true>(sm, keys, n, tile, positives, dst, nspl + 1, steps);
+    else exchange_tile<false>(sm, keys, n, tile, positives, dst, nspl + 1, steps);
+}
+
 // top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536).
 // First form: warp-aggregated atomics straight to the global bins -- 465 ms for 2 G keys on B200 (cfg-4, two
 // ranks): real score distributions put most keys into a few hundred bins, and every SM hammered the same L2
@@ -1257,5 +1397,41 @@ extern "C" int mss_eval_partition_scatter(const mss_eval_buffers *ev, int64_t n_
                         "mss_eval_partition_scatter");
     if (rc) return rc;
     MSS_CHECK_CUDA(cudaStreamSynchronize(st));     // the host staging arrays must outlive the async copies
+    return MSS_OK;
+}
+
+// Exchange by remote append: every key of this rank's evaluator is appended to the evaluator of the rank that owns its key
+// range -- dst_keys_host[d] / dst_state_host[d] are the device addresses of rank d's key buffer and state (peer-mapped
+// memory for d != this rank), each of dst_capacity keys.  One launch, no sizes needed in advance.  The caller zeroes the
+// destination states, orders the call between two barriers, and afterwards every rank reads its own state
+// (mss_eval_state_host reports a capacity overflow).  parts <= 32.  Synchronises the stream.
+extern "C" int mss_eval_exchange_append(const mss_eval_buffers *ev, int64_t n_neg, int64_t n_pos, const uint32_t *splitters_host,
+                                        int parts, const uint64_t *dst_keys_host, const uint64_t *dst_state_host,
+                                        int64_t dst_capacity, void *workspace, size_t workspace_bytes, void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= PB_MAX_PARTS, "mss_eval_exchange_append: parts must be 1..%d", PB_MAX_PARTS);
+    MSS_REQUIRE(dst_keys_host && dst_state_host && dst_capacity > 0 && workspace && workspace_bytes >= 4096,
+                "mss_eval_exchange_append: bad arguments");
+    MSS_REQUIRE(parts == 1 || splitters_host, "mss_eval_exchange_append: null splitters");
+    const uint32_t *neg, *pos;
+    MSS_REQUIRE(eval_streams(ev, n_neg, n_pos, &neg, &pos), "mss_eval_exchange_append: bad evaluator / stream sizes");
+    if (n_neg + n_pos == 0) return MSS_OK;
+    ExchangeDst dst;
+    for (int j = 0; j < PB_MAX_PARTS; j++) { dst.keys[j] = 0; dst.state[j] = 0; }
+    for (int j = 0; j < parts; j++) {
+        MSS_REQUIRE(dst_keys_host[j] && dst_state_host[j] && (dst_keys_host[j] & 15) == 0 && (dst_state_host[j] & 7) == 0,
+                    "mss_eval_exchange_append: bad destination %d", j);
+        dst.keys[j] = dst_keys_host[j];
+        dst.state[j] = dst_state_host[j];
+    }
+    dst.capacity = dst_capacity;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *spl = (uint32_t *)workspace;
+    if (parts > 1) MSS_CHECK_CUDA(cudaMemcpyAsync(spl, splitters_host, (size_t)(parts - 1) * 4, cudaMemcpyHostToDevice, st));
+    const size_t tn = sort_tiles(n_neg), tp = sort_tiles(n_pos);
+    MSS_REQUIRE(tn + tp < (1ull << 31), "mss_eval_exchange_append: too many keys");
+    exchange_append_kernel<<<(unsigned)(tn + tp), SORT_THREADS, 0, st>>>(neg, n_neg, pos, n_pos, (unsigned)tn, spl, parts - 1,
+                                                                        splitter_steps(parts), dst);
+    MSS_CHECK_LAUNCH();
+    MSS_CHECK_CUDA(cudaStreamSynchronize(st));
     return MSS_OK;
 }

@@ -153,14 +153,18 @@ class CudaBackend:
 
     # -- peer-mapped receive buffers (torch symmetric memory: every rank can store into every rank's buffer)
     def peer_alloc(self, capacity: int):
-        """Local half (may raise, e.g. out of memory): the symmetric allocation, not yet mapped by the peers."""
+        """Local half (may raise, e.g. out of memory): the symmetric allocation [keys | state], not yet mapped by the
+        peers.  The receive buffer is laid out like any evaluator buffer so that peers can APPEND to it."""
         import torch.distributed._symmetric_memory as symm
-        return symm.empty(int(capacity) * 4, dtype=torch.uint8, device=self.device)
+        kb = (int(capacity) * 4 + 255) // 256 * 256
+        return symm.empty(kb + 256, dtype=torch.uint8, device=self.device)
 
     def peer_map(self, raw, capacity: int, group):
-        """Collective half: exchange the handles.  -> dict(keys int32 [capacity], key_ptrs[world], ...)."""
+        """Collective half: exchange the handles.  -> dict(buf = PairBuffer over the local part, key_ptrs / state_ptrs =
+        every rank's addresses as mapped into this process, ...)."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
+        from .metric import PairBuffer
         grp = group if group is not None else dist.group.WORLD
         if tuple(int(x) for x in torch.__version__.split("+")[0].split(".")[:2]) < (2, 8):   # older torch: enable the group first
             try:
@@ -168,8 +172,26 @@ class CudaBackend:
             except Exception:
                 pass
         hdl = symm.rendezvous(raw, grp)
-        return {"cap": int(capacity), "raw": raw, "hdl": hdl, "keys": raw.view(torch.int32),
-                "key_ptrs": [int(p) for p in hdl.buffer_ptrs]}
+        cap = int(capacity)
+        kb = (cap * 4 + 255) // 256 * 256
+        keys = raw[: cap * 4].view(torch.int32)
+        state = raw[kb: kb + L.EVAL_STATE_BYTES]
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        return {"cap": cap, "raw": raw, "hdl": hdl, "keys": keys, "buf": PairBuffer.from_tensors(keys, state, cap),
+                "key_ptrs": ptrs, "state_ptrs": [p + kb for p in ptrs]}
+
+    def exchange_append(self, buf, n_neg: int, n_pos: int, splitters: Sequence[int], parts: int, key_ptrs: Sequence[int],
+                        state_ptrs: Sequence[int], capacity: int):
+        """Append every key of ``buf`` to the (peer-mapped) evaluator buffer of the rank owning its key range."""
+        import ctypes as C
+        lib = L.load()
+        spl = (C.c_uint32 * max(parts - 1, 1))(*[int(x) for x in splitters])
+        dk = (C.c_uint64 * parts)(*[int(x) for x in key_ptrs])
+        ds = (C.c_uint64 * parts)(*[int(x) for x in state_ptrs])
+        ws = L.workspace(4096, self.device)
+        with torch.cuda.device(self.device):
+            L.check(lib.mss_eval_exchange_append(C.byref(buf.c), n_neg, n_pos, spl, parts, dk, ds, int(capacity), ws.data_ptr(),
+                                                 4096, L.stream_ptr(self.device)), "mss_eval_exchange_append")
 
     def sort2(self, neg, n_neg: int, pos, n_pos: int):
         from .metric import sort_keys
@@ -217,9 +239,10 @@ class StreamingEvaluator:
 
     def __init__(self, capacity: int, device=None, train_id_in: int = 0, train_id_out: int = 1, backend=None,
                  distributed: Optional[bool] = None, group=None, exchange: str = "auto"):
-        """``exchange``: "p2p" = fused partition + peer-memory stores over NVLink, "nccl" = local partition +
-        all-to-all, "auto" = p2p when the backend offers peer buffers (falls back to nccl if mapping fails)."""
-        assert exchange in ("auto", "p2p", "nccl")
+        """``exchange``: "p2p" = remote append into the owners' peer-mapped buffers over NVLink (no counting pass),
+        "p2p_counted" = count + all-gather of bucket sizes + fused partition/peer stores at known offsets, "nccl" = local
+        partition + all-to-all, "auto" = p2p when the backend offers peer buffers (falls back if mapping fails)."""
+        assert exchange in ("auto", "p2p", "p2p_counted", "nccl")
         self.exchange = exchange
         self.backend = backend if backend is not None else CudaBackend(device)
         self.id_in, self.id_out = int(train_id_in), int(train_id_out)
@@ -321,57 +344,97 @@ class StreamingEvaluator:
         splitters = choose_splitters(hist.cpu().numpy(), world)
         mark("histogram_splitters")
 
-        # 3. exchange by key range, stream by stream.  Receive layout on rank r (the evaluator's own layout): negatives
-        #    from source 0, 1, ... upwards from element 0, positives from source 0, 1, ... ending at the capacity.
+        # 3. exchange by key range.  Receive layout on rank r = the evaluator's own two-stream layout.
         exchange = self.exchange
         if exchange == "auto":
-            exchange = "p2p" if hasattr(be, "peer_alloc") and not getattr(self, "_p2p_failed", False) else "nccl"
-        send = None
+            # measured on B200 / NVSwitch (cfg-4): remote append 8.6 ms vs count + scatter 10.7 ms at 2 GPUs, but 6.5 vs
+            # 5.8 ms at 8 (a remote atomic per tile and destination: 8 M of them in flight across the switch)
+            p2p = "p2p" if world <= 4 else "p2p_counted"
+            exchange = p2p if hasattr(be, "peer_alloc") and not getattr(self, "_p2p_failed", False) else "nccl"
+        r_neg = r_pos = None
         if exchange == "p2p":
-            send = list(be.partition_count2(self.buf, n_neg, n_pos, splitters, world))
-        else:
-            pk_neg, c_neg = be.partition(neg, n_neg, splitters, world)
-            pk_pos, c_pos = be.partition(pos, n_pos, splitters, world)
-            send = [c_neg, c_pos]
-            mark("partition")
-        cm = be.tensor(send[0] + send[1], torch.int64)
-        all_counts = be.empty(world * 2 * world, torch.int64)
-        dist.all_gather_into_tensor(all_counts, cm, group=g)
-        all_counts = all_counts.view(world, 2, world).cpu().numpy()       # [src, stream, dst]
-        recv_neg = [int(c) for c in all_counts[:, 0, rank]]
-        recv_pos = [int(c) for c in all_counts[:, 1, rank]]
-        m2_neg, m2_pos = int(sum(recv_neg)), int(sum(recv_pos))
-        per_dst = all_counts.sum(axis=0)                                  # [stream, dst]
-        need = int((per_dst[0] + per_dst[1]).max())                       # identical on every rank
-        pb = None
-        if exchange == "p2p":
+            # 3a. remote append: nothing is counted beforehand.  The receive capacity comes from the (sampled) global
+            #     histogram: expected keys of the fullest key range + 8 % + 64 K.
+            hn = hist.cpu().numpy().astype(np.int64)
+            bounds = [0] + [min(s >> (32 - HIST_BITS), 1 << HIST_BITS) for s in splitters] + [1 << HIST_BITS]
+            est = max(int(hn[a:b].sum()) for a, b in zip(bounds[:-1], bounds[1:])) * every
+            need = est + est // 12 + (1 << 16)
             pb = self._peer_buffers(need, g)
-            if pb is None:                                                # agreed on by all ranks: NCCL path
+            if pb is None:
                 self._p2p_failed = True
                 exchange = "nccl"
-                pk_neg, _ = be.partition(neg, n_neg, splitters, world)
-                pk_pos, _ = be.partition(pos, n_pos, splitters, world)
-                mark("partition")
             else:
-                mark("count")
-        if exchange == "p2p":
-            # 3a. fused: ONE kernel per stream partitions and stores every bucket straight into its owner's receive
-            #     buffer over NVLink (4-byte key stores only; no staging copy, no all-to-all)
-            cap = pb["cap"]
-            off_neg = [int(all_counts[:rank, 0, d].sum()) for d in range(world)]
-            off_pos = [cap - int(per_dst[1][d]) + int(all_counts[:rank, 1, d].sum()) for d in range(world)]
-            dist.barrier(group=g)                                         # peers are done with the previous contents
-            be.partition_scatter2(self.buf, n_neg, n_pos, splitters, world, pb["key_ptrs"], off_neg, off_pos)
-            dist.barrier(group=g)                                         # every rank's stores have landed
-            rk = pb["keys"]
-            r_neg, r_pos = rk[:m2_neg], rk[cap - m2_pos: cap]
-            mark("partition_scatter_p2p")
-        else:
-            # 3b. local partition by destination rank + NCCL all-to-all per stream
-            r_neg, r_pos = be.empty(max(m2_neg, 1), torch.int32)[:m2_neg], be.empty(max(m2_pos, 1), torch.int32)[:m2_pos]
-            dist.all_to_all_single(r_neg, pk_neg, recv_neg, send[0], group=g)
-            dist.all_to_all_single(r_pos, pk_pos, recv_pos, send[1], group=g)
-            mark("all_to_all")
+                rb = pb["buf"]
+                rb.reset()
+                torch.cuda.synchronize(be.device)
+                dist.barrier(group=g)                                     # every receive buffer is empty
+                be.exchange_append(self.buf, n_neg, n_pos, splitters, world, pb["key_ptrs"], pb["state_ptrs"], pb["cap"])
+                dist.barrier(group=g)                                     # every rank's appends have landed
+                try:
+                    m2, m2_pos, _, _ = rb.read_state()
+                    over = 0
+                except L.MssError:                                        # a receive buffer overflowed (estimate too small)
+                    m2 = m2_pos = 0
+                    over = 1
+                mine = be.tensor([m2 - m2_pos, m2_pos, over], torch.int64)
+                got = be.empty(3 * world, torch.int64)
+                dist.all_gather_into_tensor(got, mine, group=g)
+                got = got.view(world, 3).cpu().numpy()
+                if int(got[:, 2].max()):
+                    exchange = "p2p_counted"                              # agreed on by all ranks: exact sizes first
+                else:
+                    m2_neg = m2 - m2_pos
+                    per_dst = got[:, :2].T                                # [stream, dst]
+                    send, recv_neg, recv_pos = None, [m2_neg], [m2_pos]
+                    r_neg, r_pos = rb.streams(m2, m2_pos)
+                    mark("exchange_append_p2p")
+        if exchange in ("p2p_counted", "nccl"):
+            if exchange == "p2p_counted":
+                send = list(be.partition_count2(self.buf, n_neg, n_pos, splitters, world))
+            else:
+                pk_neg, c_neg = be.partition(neg, n_neg, splitters, world)
+                pk_pos, c_pos = be.partition(pos, n_pos, splitters, world)
+                send = [c_neg, c_pos]
+                mark("partition")
+            cm = be.tensor(send[0] + send[1], torch.int64)
+            all_counts = be.empty(world * 2 * world, torch.int64)
+            dist.all_gather_into_tensor(all_counts, cm, group=g)
+            all_counts = all_counts.view(world, 2, world).cpu().numpy()       # [src, stream, dst]
+            recv_neg = [int(c) for c in all_counts[:, 0, rank]]
+            recv_pos = [int(c) for c in all_counts[:, 1, rank]]
+            m2_neg, m2_pos = int(sum(recv_neg)), int(sum(recv_pos))
+            per_dst = all_counts.sum(axis=0)                                  # [stream, dst]
+            need = int((per_dst[0] + per_dst[1]).max())                       # identical on every rank
+            if exchange == "p2p_counted":
+                pb = self._peer_buffers(need, g)
+                if pb is None:                                                # agreed on by all ranks: NCCL path
+                    self._p2p_failed = True
+                    exchange = "nccl"
+                    pk_neg, _ = be.partition(neg, n_neg, splitters, world)
+                    pk_pos, _ = be.partition(pos, n_pos, splitters, world)
+                    mark("partition")
+                else:
+                    mark("count")
+            if exchange == "p2p_counted":
+                # 3b. fused: ONE call partitions both streams and stores every bucket straight into its owner's receive
+                #     buffer over NVLink at offsets known from the all-gathered counts
+                cap = pb["cap"]
+                off_neg = [int(all_counts[:rank, 0, d].sum()) for d in range(world)]
+                off_pos = [cap - int(per_dst[1][d]) + int(all_counts[:rank, 1, d].sum()) for d in range(world)]
+                torch.cuda.synchronize(be.device)
+                dist.barrier(group=g)                                         # peers are done with the previous contents
+                be.partition_scatter2(self.buf, n_neg, n_pos, splitters, world, pb["key_ptrs"], off_neg, off_pos)
+                dist.barrier(group=g)                                         # every rank's stores have landed
+                rk = pb["keys"]
+                r_neg, r_pos = rk[:m2_neg], rk[cap - m2_pos: cap]
+                mark("partition_scatter_p2p")
+            else:
+                # 3c. local partition by destination rank + NCCL all-to-all per stream
+                r_neg = be.empty(max(m2_neg, 1), torch.int32)[:m2_neg]
+                r_pos = be.empty(max(m2_pos, 1), torch.int32)[:m2_pos]
+                dist.all_to_all_single(r_neg, pk_neg, recv_neg, send[0], group=g)
+                dist.all_to_all_single(r_pos, pk_pos, recv_pos, send[1], group=g)
+                mark("all_to_all")
 
         # 4. local sort of both streams + merge-path counts with the global prefixes (known from the count matrix)
         be.sort2(r_neg, m2_neg, r_pos, m2_pos)

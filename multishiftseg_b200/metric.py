@@ -76,6 +76,16 @@ class PairBuffer:
         self.state = torch.zeros(L.EVAL_STATE_BYTES, dtype=torch.uint8, device=self.device)
         self.c = L.EvalBuffers(self.keys.data_ptr(), self.state.data_ptr(), self.capacity)
 
+    @classmethod
+    def from_tensors(cls, keys: torch.Tensor, state: torch.Tensor, capacity: int):
+        """Wrap existing device memory (e.g. a peer-mapped receive buffer of the multi-GPU exchange)."""
+        self = cls.__new__(cls)
+        self.device = keys.device
+        self.capacity = int(capacity)
+        self.keys, self.state = keys, state
+        self.c = L.EvalBuffers(keys.data_ptr(), state.data_ptr(), self.capacity)
+        return self
+
     def reset(self):
         with torch.cuda.device(self.device):
             L.check(L.load().mss_eval_reset(C.byref(self.c), L.stream_ptr(self.device)), "mss_eval_reset")

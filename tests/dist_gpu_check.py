@@ -31,7 +31,7 @@ def main():
         want = c_oracle.eval_ood_measure(s, l)
         one = metric.eval_ood_measure(s, l)
         one = None if one is None else tuple(float(v) for v in one)
-        for exch in ("p2p", "nccl"):          # fused peer-memory scatter, and partition + NCCL all-to-all
+        for exch in ("p2p", "p2p_counted", "nccl"):   # remote append, counted peer-memory scatter, partition + NCCL all-to-all
             ev = StreamingEvaluator(n // world + 2 * img, distributed=True, exchange=exch)
             for a, b in chunks[rank::world]:
                 ev.update(torch.from_numpy(s[a:b]).cuda(), torch.from_numpy(l[a:b]).cuda())
@@ -41,7 +41,7 @@ def main():
             ok &= good
             if rank == 0:
                 x = ev.last_exchange if good and got else {}
-                print(f"[world {world}] {mode:6s} n={n:8d} {exch:4s}->{x.get('exchange')} multi-gpu == 1-gpu == oracle: {good}  {got}  "
+                print(f"[world {world}] {mode:6s} n={n:8d} {exch:11s}->{x.get('exchange')} multi-gpu == 1-gpu == oracle: {good}  {got}  "
                       f"recv={x.get('recv_counts', '')} {x.get('p2p_error') or ''}", flush=True)
     # fused DeepLab scoring -> evaluator, sharded images
     g = torch.Generator().manual_seed(7)
