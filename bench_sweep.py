@@ -217,7 +217,7 @@ def _timed_steps(env, step, steps, warmup):
     return res, mean(times), mean(score_ms), mean(metric_ms), launches
 
 
-def run_cfg4(env, images=2000, steps=3, warmup=1, oracle_check=True):
+def run_cfg4(env, images=2000, steps=3, warmup=1, oracle_check=True, exchange="auto"):
     """cfg-4: `images` frames = images/16 copies of a 16-image pool, fused energy scoring + append per batch, ONE exact
     global metric.  Returns the result dict (rank 0; None elsewhere).  `bit_exact_vs_pool` is computed inside the run:
     sweep result == the pool evaluated once on one GPU == (oracle_check) the CPU oracle on the pool's score map."""
@@ -227,7 +227,8 @@ def run_cfg4(env, images=2000, steps=3, warmup=1, oracle_check=True):
     batches = max(1, images // POOL)
     images = batches * POOL
     my_batches = len(range(rank, batches, world))                   # batch j -> rank j % world
-    ev = StreamingEvaluator(capacity=max(my_batches, 1) * POOL * H * W, device=dev, distributed=(world > 1))
+    ev = StreamingEvaluator(capacity=max(my_batches, 1) * POOL * H * W, device=dev, distributed=(world > 1),
+                            exchange=exchange if world > 1 else "auto")
 
     def step():
         ev.reset()
@@ -272,6 +273,8 @@ def run_cfg4(env, images=2000, steps=3, warmup=1, oracle_check=True):
         out["bit_exact_vs_pool"] = bool(out["matches_single_pool"])
     if world > 1 and exchange:
         out["exchange"] = {"kind": exchange["exchange"], "recv_keys_rank0": [int(sum(c)) for c in exchange["recv_counts"]],
+                           "note": "phase_ms_rank0 are host wall-clock marks inside compute(); with kind = stream the first one "
+                                   "also waits for the scoring / exchange kernels still in flight",
                            "thresholds_per_rank": exchange["thresholds_per_rank"],
                            "phase_ms_rank0": {k: round(v, 3) for k, v in exchange.get("phase_ms", {}).items()}}
     return out
@@ -339,6 +342,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--continuous", type=int, default=0, help="also run the T ~= N metric-stage variant on this many frames")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=("auto", "stream", "p2p", "p2p_counted", "nccl"),
+                    help="multi-GPU exchange of StreamingEvaluator (stream = overlapped with the scoring)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench_sweep.py needs a B200: there is no CPU fallback for the product path")
@@ -358,7 +363,7 @@ def main():
         return main5(args, world, rank, local, dist)
 
     env = Env(dist, rank, world, local)
-    r = run_cfg4(env, args.images, args.steps, args.warmup, oracle_check=not args.no_oracle)
+    r = run_cfg4(env, args.images, args.steps, args.warmup, oracle_check=not args.no_oracle, exchange=args.exchange)
     c = run_continuous(env, args.continuous, args.steps, args.warmup) if args.continuous else None
     if rank == 0:
         line = {

@@ -894,6 +894,39 @@ exchange_append_kernel(const uint32_t *__restrict__ neg, long long n_neg, const 
     else exchange_tile<false>(sm, keys, n, tile, positives, dst, nspl + 1, steps);
 }
 
+// The same, with the stream sizes read from the source evaluator's DEVICE state: nothing on the host has to know how
+// many keys a batch produced, so a batch can be exchanged right behind the kernel that scored it, on a side stream, while
+// the next batch is being scored (StreamingEvaluator(exchange="stream")).  gridDim.x bounds the number of tiles.
+__global__ void __launch_bounds__(SORT_THREADS, 4)
+exchange_append_dev_kernel(const uint32_t *__restrict__ keys, long long capacity, const EvalState *__restrict__ state,
+                           const uint32_t *__restrict__ splitters, int nspl, int steps, ExchangeDst dst) {
+    __shared__ PartSmem sm;
+    const unsigned tid = threadIdx.x;
+    const long long n_neg = (long long)min(state->n_neg, (unsigned long long)capacity);
+    const long long n_pos = (long long)min(state->n_pos, (unsigned long long)(capacity - n_neg));
+    const unsigned tiles_neg = (unsigned)((n_neg + SORT_TILE - 1) / SORT_TILE), tiles_pos = (unsigned)((n_pos + SORT_TILE - 1) / SORT_TILE);
+    if (blockIdx.x >= tiles_neg + tiles_pos) return;
+    if (tid < SORT_WARPS * PB_MAX_PARTS) (&sm.warp_hist[0][0])[tid] = 0;
+    if ((int)tid < nspl) sm.spl[tid] = __ldg(splitters + tid);
+    __syncthreads();
+    const bool positives = blockIdx.x >= tiles_neg;
+    const unsigned tile = positives ? blockIdx.x - tiles_neg : blockIdx.x;
+    const uint32_t *src = positives ? keys + (capacity - n_pos) : keys;
+    const long long n = positives ? n_pos : n_neg;
+    if ((long long)(tile + 1) * SORT_TILE <= n) exchange_tile<true>(sm, src, n, tile, positives, dst, nspl + 1, steps);
+    else exchange_tile<false>(sm, src, n, tile, positives, dst, nspl + 1, steps);
+}
+
+// accum += staging (counts, flags); staging = 0 -- the staging buffer is empty again for the next batch
+__global__ void eval_state_fold_kernel(EvalState *accum, EvalState *staging) {
+    accum->n_neg += staging->n_neg;
+    accum->n_pos += staging->n_pos;
+    accum->nan_flag |= staging->nan_flag;
+    accum->inf_flag |= staging->inf_flag;
+    accum->overflow += staging->overflow;
+    staging->n_neg = 0; staging->n_pos = 0; staging->nan_flag = 0; staging->inf_flag = 0; staging->overflow = 0;
+}
+
 // top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536).
 // First form: warp-aggregated atomics straight to the global bins -- 465 ms for 2 G keys on B200 (cfg-4, two
 // ranks): real score distributions put most keys into a few hundred bins, and every SM hammered the same L2
@@ -1433,5 +1466,35 @@ extern "C" int mss_eval_exchange_append(const mss_eval_buffers *ev, int64_t n_ne
                                                                         splitter_steps(parts), dst);
     MSS_CHECK_LAUNCH();
     MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    return MSS_OK;
+}
+
+// Streaming form: enqueue (no host synchronisation) the exchange of a STAGING evaluator -- its sizes are read from its
+// device state -- followed by `accum_state += staging state; staging state = 0`.  splitters_dev is a DEVICE array.
+extern "C" int mss_eval_exchange_stream(const mss_eval_buffers *staging, const uint32_t *splitters_dev, int parts,
+                                        const uint64_t *dst_keys_host, const uint64_t *dst_state_host, int64_t dst_capacity,
+                                        void *accum_state, void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= PB_MAX_PARTS, "mss_eval_exchange_stream: parts must be 1..%d", PB_MAX_PARTS);
+    MSS_REQUIRE(staging && staging->keys && staging->state && staging->capacity > 0 && accum_state && dst_keys_host &&
+                    dst_state_host && dst_capacity > 0 && (parts == 1 || splitters_dev),
+                "mss_eval_exchange_stream: bad arguments");
+    ExchangeDst dst;
+    for (int j = 0; j < PB_MAX_PARTS; j++) { dst.keys[j] = 0; dst.state[j] = 0; }
+    for (int j = 0; j < parts; j++) {
+        MSS_REQUIRE(dst_keys_host[j] && dst_state_host[j] && (dst_keys_host[j] & 15) == 0 && (dst_state_host[j] & 7) == 0,
+                    "mss_eval_exchange_stream: bad destination %d", j);
+        dst.keys[j] = dst_keys_host[j];
+        dst.state[j] = dst_state_host[j];
+    }
+    dst.capacity = dst_capacity;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tiles = sort_tiles(staging->capacity) + 2;            // two streams: up to one partial tile each
+    MSS_REQUIRE(tiles < (1ull << 31), "mss_eval_exchange_stream: staging buffer too large");
+    exchange_append_dev_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(staging->keys, staging->capacity,
+                                                                        (const EvalState *)staging->state, splitters_dev,
+                                                                        parts - 1, splitter_steps(parts), dst);
+    MSS_CHECK_LAUNCH();
+    eval_state_fold_kernel<<<1, 1, 0, st>>>((EvalState *)accum_state, (EvalState *)staging->state);
+    MSS_CHECK_LAUNCH();
     return MSS_OK;
 }

@@ -193,6 +193,18 @@ class CudaBackend:
             L.check(lib.mss_eval_exchange_append(C.byref(buf.c), n_neg, n_pos, spl, parts, dk, ds, int(capacity), ws.data_ptr(),
                                                  4096, L.stream_ptr(self.device)), "mss_eval_exchange_append")
 
+    def exchange_stream(self, buf, spl_dev: torch.Tensor, parts: int, key_ptrs: Sequence[int], state_ptrs: Sequence[int],
+                        capacity: int, accum_state: torch.Tensor):
+        """Enqueue (no host sync, current stream) the remote append of a staging buffer -- sizes are read from its device
+        state -- and fold its state into ``accum_state``."""
+        import ctypes as C
+        lib = L.load()
+        dk = (C.c_uint64 * parts)(*[int(x) for x in key_ptrs])
+        ds = (C.c_uint64 * parts)(*[int(x) for x in state_ptrs])
+        with torch.cuda.device(self.device):
+            L.check(lib.mss_eval_exchange_stream(C.byref(buf.c), spl_dev.data_ptr(), parts, dk, ds, int(capacity),
+                                                 accum_state.data_ptr(), L.stream_ptr(self.device)), "mss_eval_exchange_stream")
+
     def sort2(self, neg, n_neg: int, pos, n_pos: int):
         from .metric import sort_keys
         sort_keys(neg, n_neg, pos, n_pos)
@@ -238,52 +250,213 @@ class StreamingEvaluator:
     torch.distributed is initialised; single-process otherwise)."""
 
     def __init__(self, capacity: int, device=None, train_id_in: int = 0, train_id_out: int = 1, backend=None,
-                 distributed: Optional[bool] = None, group=None, exchange: str = "auto"):
-        """``exchange``: "p2p" = remote append into the owners' peer-mapped buffers over NVLink (no counting pass),
+                 distributed: Optional[bool] = None, group=None, exchange: str = "auto", stage_capacity: Optional[int] = None):
+        """``exchange``: "stream" = every batch is exchanged (remote append over NVLink) on a side stream right behind the
+        kernel that scored it, while the next batch is scored -- ``compute`` then starts with the keys already at their
+        owners.  The key ranges are fixed from the FIRST batch (a collective inside the first ``update*`` call: every
+        rank must make one), ``reset`` is collective, and a rank receives about ``capacity`` keys (+25 %).
+        "p2p" = remote append into the owners' peer-mapped buffers over NVLink (no counting pass),
         "p2p_counted" = count + all-gather of bucket sizes + fused partition/peer stores at known offsets, "nccl" = local
         partition + all-to-all, "auto" = p2p when the backend offers peer buffers (falls back if mapping fails)."""
-        assert exchange in ("auto", "p2p", "p2p_counted", "nccl")
+        assert exchange in ("auto", "p2p", "p2p_counted", "nccl", "stream")
         self.exchange = exchange
+        self.capacity = int(capacity)
+        self.stage_capacity = stage_capacity
+        self._st = None                  # state of the streaming exchange (exchange="stream")
         self.backend = backend if backend is not None else CudaBackend(device)
         self.id_in, self.id_out = int(train_id_in), int(train_id_out)
-        self.buf = self.backend.new_buffer(int(capacity))
-        self.buf.reset()
         self.group = group
         if distributed is None:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.distributed = bool(distributed)
+        # (a streaming evaluator keeps nothing locally: batches go through two small staging buffers to their owners)
+        self.buf = self.backend.new_buffer(1 if self._streaming() else int(capacity))
+        self.buf.reset()
+
+    _tags = 0
+
+    @staticmethod
+    def _next_tag():
+        # evaluators are created in the same order on every rank, so the n-th streaming evaluator has tag n everywhere
+        StreamingEvaluator._tags += 1
+        return "stream%d" % StreamingEvaluator._tags
 
     # ------------------------------------------------------------------ accumulation
     def reset(self):
+        """Empty the evaluator (collective in "stream" mode: every rank's receive buffer is emptied behind a barrier)."""
         self.buf.reset()
+        if self._st is not None:
+            self._stream_reset()
 
     def update(self, scores, labels):
         """One batch of score / label maps (any shape, same number of elements)."""
+        if self._streaming():
+            n = int(np.prod(np.shape(scores))) if not isinstance(scores, torch.Tensor) else scores.numel()
+            b, buf = self._stage(n)
+            self.backend.append(buf, scores, labels, self.id_in, self.id_out)
+            self._stream_push(b)
+            return
         self.backend.append(self.buf, scores, labels, self.id_in, self.id_out)
 
     def update_from_logits(self, logits: torch.Tensor, labels: torch.Tensor, key: str = "energy",
                            which: Sequence[str] = ("energy",)):
         """DeepLab fused path: score maps + ignore masking + key build in ONE kernel (deeplab.score_maps)."""
         from .deeplab import score_maps
+        if self._streaming():
+            b, buf = self._stage(labels.numel())
+            out = score_maps(logits, which, labels=labels, evaluator=buf, key=key, id_in=self.id_in, id_out=self.id_out)
+            self._stream_push(b)
+            return out
         return score_maps(logits, which, labels=labels, evaluator=self.buf, key=key, id_in=self.id_in,
                           id_out=self.id_out)
+
+    # ------------------------------------------------------------------ streaming exchange
+    def _streaming(self) -> bool:
+        return self.exchange == "stream" and self.distributed
+
+    def _stage(self, numel: int):
+        """-> (index, staging buffer) that the current stream may append ``numel`` pixels into."""
+        be = self.backend
+        if self._st is None:
+            cap = int(self.stage_capacity or numel)
+            dev = be.device
+            self._st = {"staging": [be.new_buffer(cap), be.new_buffer(cap)], "cap": cap, "n": 0, "calibrated": False,
+                        "accum": torch.zeros(L.EVAL_STATE_BYTES, dtype=torch.uint8, device=dev),
+                        "side": torch.cuda.Stream(device=dev, priority=-1),
+                        "appended": [torch.cuda.Event(), torch.cuda.Event()], "done": [None, None]}
+            for sb in self._st["staging"]:
+                sb.reset()
+        st = self._st
+        if numel > st["cap"]:
+            raise L.MssError(f"batch of {numel} pixels exceeds the staging capacity {st['cap']} (pass stage_capacity=)")
+        b = st["n"] & 1
+        st["n"] += 1
+        if st["done"][b] is not None:                                     # the exchange that last read this buffer
+            torch.cuda.current_stream(be.device).wait_event(st["done"][b])
+        return b, st["staging"][b]
+
+    def _stream_calibrate(self, buf):
+        """Collective, once: key ranges from the first batch, receive buffers, everything emptied behind a barrier."""
+        import torch.distributed as dist
+        be, g, st = self.backend, self.group, self._st
+        world = dist.get_world_size(g)
+        m, n_pos, _, _ = be.state(buf)
+        tot = be.tensor([m, self.capacity], torch.int64)
+        dist.all_reduce(tot, group=g)
+        M, total_cap = (int(v) for v in tot.tolist())
+        neg, pos = be.streams(buf, m, n_pos)
+        every = max(1, M // (world << SAMPLE_LOG2))
+        hist = be.histogram(neg, m - n_pos, HIST_BITS, every)
+        if n_pos:
+            hist = hist + be.histogram(pos, n_pos, HIST_BITS, every)
+        dist.all_reduce(hist, group=g)
+        splitters = choose_splitters(hist.cpu().numpy(), world)
+        need = total_cap // world + total_cap // (4 * world) + (1 << 20)
+        self._stream_tag = getattr(self, "_stream_tag", None) or StreamingEvaluator._next_tag()
+        pb = self._peer_buffers(need, g, tag=self._stream_tag)
+        if pb is None:
+            raise L.MssError('exchange="stream" needs peer-mapped memory: ' + str(getattr(self, "p2p_error", "")))
+        st["pb"], st["splitters"] = pb, splitters
+        st["spl_dev"] = torch.from_numpy(np.asarray(list(splitters) + [0], dtype=np.uint32).view(np.int32)).to(be.device)
+        pb["buf"].reset()
+        torch.cuda.synchronize(be.device)
+        dist.barrier(group=g)
+        st["calibrated"] = True
+
+    def _stream_push(self, b: int):
+        import torch.distributed as dist
+        be, st = self.backend, self._st
+        if not st["calibrated"]:
+            self._stream_calibrate(st["staging"][b])
+        cur = torch.cuda.current_stream(be.device)
+        st["appended"][b].record(cur)
+        st["side"].wait_event(st["appended"][b])
+        world = dist.get_world_size(self.group)
+        pb = st["pb"]
+        with torch.cuda.stream(st["side"]):
+            be.exchange_stream(st["staging"][b], st["spl_dev"], world, pb["key_ptrs"], pb["state_ptrs"], pb["cap"], st["accum"])
+            ev = torch.cuda.Event()
+            ev.record(st["side"])
+        st["done"][b] = ev
+
+    def _stream_reset(self):
+        import torch.distributed as dist
+        be, st = self.backend, self._st
+        st["side"].synchronize()
+        st["n"] = 0
+        st["done"] = [None, None]
+        st["accum"].zero_()
+        for sb in st["staging"]:
+            sb.reset()
+        if st["calibrated"]:
+            st["pb"]["buf"].reset()
+            torch.cuda.synchronize(be.device)
+            dist.barrier(group=self.group)                                # nobody appends into a buffer that is being emptied
 
     # ------------------------------------------------------------------ result
     def compute(self, recall_level: float = 0.95):
         be = self.backend
         if not self.distributed:
             return be.finish_local(self.buf, recall_level)
+        if self._streaming():
+            return self._compute_streamed(recall_level)
         m, n_pos, nan, inf = be.state(self.buf)
         return self._compute_distributed(m, n_pos, nan, inf, recall_level)
 
-    def _peer_buffers(self, need: int, g):
+    def _compute_streamed(self, recall_level):
+        """exchange="stream": the keys are already at their owners; what is left is sort + counts + tail."""
+        import time
+        import torch.distributed as dist
+        be, g, st = self.backend, self.group, self._st
+        world, rank = dist.get_world_size(g), dist.get_rank(g)
+        marks = [("start", time.perf_counter())]
+
+        def mark(name):
+            torch.cuda.synchronize(be.device)
+            marks.append((name, time.perf_counter()))
+
+        if st is None or not st["calibrated"]:
+            raise L.MssError('exchange="stream": compute() before any update (every rank must feed at least one batch)')
+        st["side"].synchronize()
+        torch.cuda.synchronize(be.device)
+        dist.barrier(group=g)                                             # every rank's appends have landed
+        acc = st["accum"].cpu().numpy()
+        n_neg, n_pos = (int(v) for v in acc[:16].view(np.uint64))
+        nan, inf = (int(v) for v in acc[16:24].view(np.uint32))
+        dropped = int(acc[24:32].view(np.uint64)[0])
+        try:
+            m2, m2_pos, _, _ = st["pb"]["buf"].read_state()
+            over = 0
+        except L.MssError:
+            m2 = m2_pos = 0
+            over = 1
+        mine = be.tensor([n_neg + n_pos, n_pos, nan, inf, m2 - m2_pos, m2_pos, over + (1 if dropped else 0)], torch.int64)
+        got = be.empty(7 * world, torch.int64)
+        dist.all_gather_into_tensor(got, mine, group=g)
+        got = got.view(world, 7).cpu().numpy()
+        M, P, gnan, ginf = (int(v) for v in got[:, :4].sum(axis=0))
+        if int(got[:, 6].max()):
+            raise L.MssError('exchange="stream": a staging or receive buffer overflowed (the key ranges fixed from the first '
+                             'batch did not balance this dataset): raise capacity / stage_capacity, or use exchange="p2p"')
+        if P == 0 or P == M:
+            return None
+        _raise_nonfinite(gnan, ginf)
+        mark("barrier_and_sizes")
+        per_dst = got[:, 4:6].T                                           # [stream, dst]
+        r_neg, r_pos = st["pb"]["buf"].streams(m2, m2_pos)
+        return self._sort_count_tail(r_neg, m2 - m2_pos, r_pos, m2_pos, per_dst, recall_level, marks, mark,
+                                     {"send_counts": None, "recv_counts": [[m2 - m2_pos], [m2_pos]],
+                                      "splitters": st["splitters"], "exchange": "stream"})
+
+    def _peer_buffers(self, need: int, g, tag=None):
         """Peer-mapped receive buffer of >= need keys on every rank, or None (on EVERY rank) if it cannot be had.
         Capability and the local allocation are agreed on with a cheap collective BEFORE the collective handle
         exchange, so a rank that fails (no peer access, out of memory) cannot leave the others blocked in it."""
         import torch.distributed as dist
         be = self.backend
         grp = g if g is not None else dist.group.WORLD
-        ck = (str(getattr(be, "device", "cpu")), getattr(grp, "group_name", None) or id(grp))
+        # (a streaming evaluator keeps its receive buffer for a whole round: it gets one of its own, `tag`)
+        ck = (str(getattr(be, "device", "cpu")), getattr(grp, "group_name", None) or id(grp), tag)
         cached = _PEER_CACHE.get(ck)
         # `need` comes from all-gathered counts and every rank has taken the same decisions before, so the cache state
         # is the same everywhere; the MIN all-reduce makes that an agreement instead of an assumption
@@ -436,6 +609,14 @@ class StreamingEvaluator:
                 dist.all_to_all_single(r_pos, pk_pos, recv_pos, send[1], group=g)
                 mark("all_to_all")
 
+        return self._sort_count_tail(r_neg, m2_neg, r_pos, m2_pos, per_dst, recall_level, marks, mark,
+                                     {"send_counts": send, "recv_counts": [recv_neg, recv_pos], "splitters": splitters,
+                                      "exchange": exchange})
+
+    def _sort_count_tail(self, r_neg, m2_neg, r_pos, m2_pos, per_dst, recall_level, marks, mark, info):
+        import torch.distributed as dist
+        be, g = self.backend, self.group
+        world, rank = dist.get_world_size(g), dist.get_rank(g)
         # 4. local sort of both streams + merge-path counts with the global prefixes (known from the count matrix)
         be.sort2(r_neg, m2_neg, r_pos, m2_pos)
         mark("sort")
@@ -465,10 +646,9 @@ class StreamingEvaluator:
         mark("gather_thresholds")
         res = be.tail(tps_all, fps_all, recall_level)
         mark("tail")
-        self.last_exchange = {"send_counts": send, "recv_counts": [recv_neg, recv_pos], "splitters": splitters,
-                              "thresholds_per_rank": Ts, "exchange": exchange,
-                              "p2p_error": getattr(self, "p2p_error", None),
-                              "phase_ms": {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}}
+        info.update({"thresholds_per_rank": Ts, "p2p_error": getattr(self, "p2p_error", None),
+                     "phase_ms": {n: (t - marks[i][1]) * 1e3 for i, (n, t) in enumerate(marks[1:])}})
+        self.last_exchange = info
         return res
 
 

@@ -43,6 +43,23 @@ def main():
                 x = ev.last_exchange if good and got else {}
                 print(f"[world {world}] {mode:6s} n={n:8d} {exch:11s}->{x.get('exchange')} multi-gpu == 1-gpu == oracle: {good}  {got}  "
                       f"recv={x.get('recv_counts', '')} {x.get('p2p_error') or ''}", flush=True)
+    # streaming exchange: every batch goes to its owners right behind its append (key ranges fixed from the first batch)
+    for ci, (mode, n, p_ood, p_ign) in enumerate(cases[:4]):
+        s, l = gi.metric_case(500 + ci, n, mode, p_ood, p_ign, label_dtype="uint8")
+        img = max(n // 16, 1)
+        chunks = [(i, min(i + img, n)) for i in range(0, n, img)]
+        want = c_oracle.eval_ood_measure(s, l)
+        ev = StreamingEvaluator(n // world + 2 * img, distributed=True, exchange="stream", stage_capacity=img + 16)
+        for rep in range(2):                                   # a second round after reset() reuses ranges and buffers
+            ev.reset()
+            for a, b in chunks[rank::world]:
+                ev.update(torch.from_numpy(s[a:b]).cuda(), torch.from_numpy(l[a:b]).cuda())
+            got = ev.compute()
+            got = None if got is None else tuple(float(v) for v in got)
+            good = got == want
+            ok &= good
+            if rank == 0:
+                print(f"[world {world}] {mode:6s} n={n:8d} stream round {rep} multi-gpu == oracle: {good}  {got}", flush=True)
     # fused DeepLab scoring -> evaluator, sharded images
     g = torch.Generator().manual_seed(7)
     B, H, W = 4, 128, 256
