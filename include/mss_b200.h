@@ -206,6 +206,17 @@ MSS_API size_t mss_ood_metrics_from_eval_workspace_bytes(int64_t count);
 MSS_API int mss_ood_metrics_from_eval(const mss_eval_buffers *ev, void *workspace, size_t workspace_bytes,
                               double out_host[3], int64_t counts_host[4], void *stream);
 
+/* The multi-GPU form of the same: one process or thread per GPU, each holding the keys of ITS images in an
+ * evaluator; every rank calls this with the same NCCL communicator and gets the metrics of the WHOLE dataset,
+ * bit-identical to the single-GPU result (key-range exchange: all-reduce of a sampled key histogram -> splitters, local
+ * partition + ncclSend/ncclRecv, local sort + merge-path counts with integer prefixes, all-gather of the per-threshold
+ * counts, identical float64 tail).  nccl_comm is an ncclComm_t; NCCL is resolved at run time from the caller's process
+ * (the library is not linked against it): MSS_ERR_UNSUPPORTED if it is not loaded.  Temporaries are taken from and
+ * returned to the stream-ordered allocator (cudaMallocAsync) inside the call.  The evaluator's keys are left untouched.
+ * Returns like mss_ood_metrics (MSS_EMPTY_CLASS / MSS_ERR_NAN / MSS_ERR_INF decided on the GLOBAL dataset). */
+MSS_API int mss_ood_metrics_dist(const mss_eval_buffers *ev, void *nccl_comm, int rank, int world, double out_host[3],
+                         int64_t counts_host[4], void *stream);
+
 /* ---- stage-level entry points (used by the multi-GPU evaluator, which interleaves them with
  * collectives issued through torch.distributed) ------------------------------------------------ */
 /* stable LSD radix sort (onesweep, key-only) of two independent key arrays, ascending, in place, by one sequence

@@ -69,6 +69,7 @@ SIGNATURES = {
     "mss_ood_metrics": (_i, [_p, _p, _i, _i64, _i64, _i64, _p, _sz, _p, _p, _p]),
     "mss_ood_metrics_from_eval_workspace_bytes": (_sz, [_i64]),
     "mss_ood_metrics_from_eval": (_i, [_EV, _p, _sz, _p, _p, _p]),
+    "mss_ood_metrics_dist": (_i, [_EV, _p, _i, _i, _p, _p, _p]),
     "mss_sort_keys_workspace_bytes": (_sz, [_i64]),
     "mss_sort_keys": (_i, [_p, _i64, _p, _i64, _p, _sz, _p]),
     "mss_eval_sort": (_i, [_EV, _i64, _p, _sz, _p]),

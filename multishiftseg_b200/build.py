@@ -20,7 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-          "-I", INCLUDE] + os.environ.get("MSS_NVCC_EXTRA", "").split()      # e.g. -DTQ_EXPERIMENT=1 (kernel experiments)
+          "-I", INCLUDE] + os.environ.get("MSS_NVCC_EXTRA", "").split()      # e.g. -DTQ_RCP_PAIR=1 (documented kernel switches)
 # per-file flags: the float64 metric tail must round every product and sum separately (numpy does)
 PER_FILE = {"metrics.cu": ["-fmad=false"]}
 

@@ -1,6 +1,10 @@
 // Mask2Former fused post-head inference, tcgen05 variant with SHARED TAPS (exact x4 upsample path) -- the
 // default fast path.  Same contract as the other x4 kernels.
 //
+// (Round-1 timing experiments -- dropping either MUFU op of the sigmoid 146 -> 118 us/image, one TMEM store instead of
+// four: no change, a quarter of the MMAs: -17 % before the elect_one fix, none after -- were run with compile-time
+// switches that have since been removed from this file; their results are in DESIGN.md section 4.)
+//
 // ncu on the first tcgen05 kernel (m2f_tc5.cuh, round 1, 204 us/image): 22.9 warp instructions per
 // (pixel, query): 4 LDS + 8 FMA-pipe ops of bilinear interpolation, 5 of sigmoid + TF32 split, ~5 of address /
 // loop / barrier overhead; issue slots 68 % busy, MUFU pipe 50 %.  With x4 upsampling (align_corners=False)
@@ -33,10 +37,6 @@
 // TMEM: D tiles at columns 0..127, A buffers at 128..255 (per buffer: tile i, half h at i*16 + 8*h)
 //   -> 256 columns per CTA, two CTAs per SM.
 #pragma once
-
-#ifndef TQ_EXPERIMENT
-#define TQ_EXPERIMENT 0     /* 1..3: timing experiments (wrong results), see scratch/gpu_m2f_exp.sh */
-#endif
 
 namespace mss {
 
@@ -273,20 +273,12 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
 #else
                             if (j > 0) {
 #endif
-#if TQ_EXPERIMENT == 1 || TQ_EXPERIMENT == 4     /* timing experiment: no MUFU / no rcp */
-                                sg = fmaf(ex[i], 0.25f, 0.5f);
-#else
                                 if (i < TQ_RCP_FMA) sg = rcp_fma(1.0f + ex[i]);
                                 else asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex[i]));
-#endif
                             }
                             if (j < 4) {
-#if TQ_EXPERIMENT == 1 || TQ_EXPERIMENT == 5     /* no MUFU / no ex2 */
-                                ex[i] = e[i] * e[i];
-#else
                                 // (the FMA-pipe reciprocal needs a finite 1 + 2^e: clamp e, i.e. mask logits below -87)
                                 asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex[i]) : "f"(TQ_RCP_PAIR ? fminf(e[i], 63.f) : (i < TQ_RCP_FMA ? fminf(e[i], 126.f) : e[i])));
-#endif
                             }
                             if (j > 0) {
                                 const int jq = j - 1;
@@ -305,15 +297,8 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                     // the values are ready: only now wait for the MMAs of use u-2 to have read this A buffer
                     if (u >= 2) mbar_wait(&bar_empty[slot], ((u >> 1) + 1) & 1);
                     tc5_fence_after();
-#if TQ_EXPERIMENT == 2      /* timing experiment: one TMEM store instead of four */
-                    { uint32_t w8[8];
-#pragma unroll
-                      for (int k = 0; k < 8; k++) w8[k] = v[0][k] ^ v[1][k] ^ v[2][k] ^ v[3][k];
-                      tc5_st8(a_base, w8); }
-#else
 #pragma unroll
                     for (int i = 0; i < 4; i++) tc5_st8(a_base + i * 16, v[i]);
-#endif
                 } else {
                     // padded queries: the box holds the next image's masks there; they must not reach the MMA
                     if (u >= 2) mbar_wait(&bar_empty[slot], ((u >> 1) + 1) & 1);
@@ -352,7 +337,7 @@ m2f_tc5q_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                         const uint64_t dh = tc5_smem_desc(bhi + (2 * ks + hh) * CHUNK, LBO, 128);
                         const uint64_t dl = tc5_smem_desc(blo + (2 * ks + hh) * CHUNK, LBO, 128);
 #pragma unroll
-                        for (int i = 0; i < (TQ_EXPERIMENT == 3 ? 1 : 4); i++) {      /* experiment 3: a quarter of the MMAs */
+                        for (int i = 0; i < 4; i++) {
                             const uint32_t d = tmem_u + TQ_COL_D + i * 32, a = tmem_u + TQ_COL_A + slot * 64 + i * 16 + hh * 8;
                             tc5_mma_ts(d, a, dh, T5_IDESC, (ks | hh) > 0);
                             tc5_mma_ts(d, a, dl, T5_IDESC, 1);

@@ -48,3 +48,9 @@ def test_multi_gpu_bit_exact():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    # the same through the C entry point a C / C++ binder would call (its own ncclComm_t)
+    cmd[-1] = os.path.join(ROOT, "tests", "dist_c_abi_check.py")
+    cmd[cmd.index("29533")] = "29534"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -4,6 +4,7 @@ N=$1; TAG=$2
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_n$N.txt 2>&1
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py > gpurun_out/dist_check_n${N}_$TAG.log 2>&1; echo "dist_check rc=$?"; grep -v "^W\|^\[W\|warn" gpurun_out/dist_check_n${N}_$TAG.log | tail -16
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 tests/dist_c_abi_check.py > gpurun_out/dist_c_abi_n${N}_$TAG.log 2>&1; echo "c_abi rc=$?"; grep "C ABI\|rror" gpurun_out/dist_c_abi_n${N}_$TAG.log | tail -8
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n${N}_$TAG.json 2> gpurun_out/bench_n${N}_$TAG.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_n${N}_$TAG.err
 python - <<PY
 import json
