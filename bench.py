@@ -310,6 +310,19 @@ def extra_m2f(batch=8):
         flop = px * (2 * 100 * 19)                       # contraction only (3 800 flop/px)
         out[name] = {"ms": ms, "mpix_s": px / ms / 1e3, "images_s": batch / ms * 1e3,
                      "contraction_TFLOPs": flop / ms / 1e9}
+    # the reference evaluates one image per call (exps/M2F.yaml:21, valid_batch 1): 1056 CTAs on 296 slots = 3.6 waves
+    cls1, lo1 = cls[:1].contiguous(), lo[:1].contiguous()
+    for _ in range(3):
+        m2f.anomaly_score_from_lowres(cls1, lo1, (H, W), (H, W))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        m2f.anomaly_score_from_lowres(cls1, lo1, (H, W), (H, W))
+    e1.record()
+    torch.cuda.synchronize()
+    out["anomaly_score_batch1"] = {"us_per_image": e0.elapsed_time(e1) / 20 * 1e3, "launches_per_call": 2,
+                                   "note": "device time of back-to-back calls (class-probability table kernel + main kernel)"}
     out["workload"] = f"cfg3: M2F semantic_inference Q=100 C=19+1 256x512->1024x2048 batch {batch}"
     out["fma_roofline_TFLOPs"] = 148 * 128 * 2 * 1.965e9 / 1e12
     # binding pipe of the tcgen05 kernel: the two MUFU ops (ex2 + rcp) of each of the Q sigmoids per pixel,
@@ -317,6 +330,48 @@ def extra_m2f(batch=8):
     floor_ms = 2 * 100 * batch * H * W / (16 * 148 * 1.965e9) * 1e3
     out["mufu_floor_ms"] = floor_ms
     out["frac_of_mufu_roofline"] = floor_ms / out["anomaly_score"]["ms"]
+    return out
+
+
+def extra_m2f_chain():
+    """SURVEY 8f-1, Mask2Former half: is fusing the mask-logit GEMM INTO the semantic-inference kernel worth it?  The
+    two-launch chain writes the decoder-resolution masks once (52 MB per image) and reads them back.  Measured here: the
+    chain per image at batch 8 (intermediate through HBM: 420 MB per batch > L2) and at batch 1 (the 52 MB intermediate
+    stays in the 126 MB L2 -- the traffic a fused kernel would save is already off the DRAM path), beside its two parts."""
+    from multishiftseg_b200 import m2f
+    g = torch.Generator(device="cuda").manual_seed(7100)
+    out = {}
+
+    def ms_of(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for B in (8, 1):
+        feat = torch.randn((B, 256, 256, 512), device="cuda", generator=g)
+        emb = torch.randn((B, 100, 256), device="cuda", generator=g) / 16
+        cls = 3.0 * torch.randn((B, 100, 20), device="cuda", generator=g)
+        lo = m2f.mask_logits(emb, feat)
+        t_gemm = ms_of(lambda: m2f.mask_logits(emb, feat))
+        t_sem = ms_of(lambda: m2f.anomaly_score_from_lowres(cls, lo, (H, W), (H, W)))
+        t_chain = ms_of(lambda: m2f.anomaly_score_from_features(cls, emb, feat, (H, W), (H, W)))
+        out[f"batch{B}"] = {"mask_gemm_us_per_image": t_gemm * 1e3 / B, "semantic_us_per_image": t_sem * 1e3 / B,
+                            "chain_us_per_image": t_chain * 1e3 / B,
+                            "intermediate_MB": B * 100 * 256 * 512 * 4 / 1e6}
+        del feat, emb, cls, lo
+    b8, b1 = out["batch8"], out["batch1"]
+    # what removing the intermediate's DRAM round trip can be worth at most: its bytes (written + read) at the HBM peak
+    peak, _, _ = peaks()
+    out["intermediate_round_trip_us_per_image_at_hbm_peak"] = 2 * 100 * 256 * 512 * 4 / peak / 1e3
+    out["chain_minus_parts_us_per_image_batch8"] = b8["chain_us_per_image"] - b8["mask_gemm_us_per_image"] - b8["semantic_us_per_image"]
+    out["workload"] = "anomaly_score_from_features: mask_embed x mask_features -> masks 256x512 -> fused upsample/sigmoid/contraction/1-max 1024x2048"
     return out
 
 
@@ -703,7 +758,8 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_extra:
         try:
-            extra.update({"metrics": extra_metrics_stage(), "m2f": extra_m2f(), "confusion": extra_confusion(),
+            extra.update({"metrics": extra_metrics_stage(), "m2f": extra_m2f(), "m2f_chain": extra_m2f_chain(),
+                          "confusion": extra_confusion(),
                           "head": extra_head(), "mask_gemm": extra_mask_gemm(), "backward": extra_backward()})
         except Exception as e:
             extra["error"] = repr(e)

@@ -171,6 +171,19 @@ MSS_API int mss_m2f_semantic_inference(const float *cls_logits, const float *mas
                                const int32_t *keep_count, float *extra, int64_t extra_batch_stride,
                                void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
 
+/* (Mask2Former half) backward of the fused anomaly score of mss_m2f_semantic_inference, for the
+ * trainer's use of the same path with autograd (train_m2f.py:443 calls get_anomaly_score :387-407 inside the step; its
+ * result feeds criterion.loss_ood, modeling/criterion.py:128-187, and lib/loss.py:119-147):
+ *   grad_score [B, Hc, Wc] = dL/d(1 - max_c sum_q softmax(cls)[q,c] sigmoid(upsample(mask_logits))[q,px])
+ *   grad_cls   [B, Q, C+1] = dL/dcls_logits     grad_masks [B, Q, h, w] = dL/dmask_logits (decoder resolution)
+ * torch.max semantics (gradient to the first maximal class), exact adjoint of the align_corners=False upsample, no
+ * atomics: deterministic.  The [Q, Hp, Wp] tensors are never materialised.  Q <= 128, C < 32.
+ * workspace: mss_m2f_anomaly_backward_workspace_bytes(B, Q, C, Hc, Wc). */
+MSS_API size_t mss_m2f_anomaly_backward_workspace_bytes(int64_t B, int Q, int C, int Hc, int Wc);
+MSS_API int mss_m2f_anomaly_backward(const float *cls_logits, const float *mask_logits, const float *grad_score, int64_t B,
+                             int Q, int C, int h, int w, int Hp, int Wp, int Hc, int Wc, float *grad_cls,
+                             float *grad_masks, void *workspace, size_t workspace_bytes, void *stream);
+
 /* (Mask2Former half) the mask-logit contraction in front of the scoring path,
  * lib/network/mask2former/modeling/transformer_decoder/mask2former_transformer_decoder.py:528-529 (pred_masks)
  * and :548-549 (pred_masks_ood):   outputs_mask = torch.einsum("bqc,bchw->bqhw", mask_embed, mask_features)

@@ -63,6 +63,8 @@ SIGNATURES = {
     "mss_m2f_workspace_bytes": (_sz, [_i64, _i, _i]),
     "mss_m2f_semantic_inference": (_i, [_p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p,
                                         _p, _i64, _p, _sz, _u, _p]),
+    "mss_m2f_anomaly_backward_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
+    "mss_m2f_anomaly_backward": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "mss_m2f_mask_logits_workspace_bytes": (_sz, [_i64, _i]),
     "mss_m2f_mask_logits": (_i, [_p, _p, _i64, _i, _i, _i64, _p, _p, _sz, _p]),
     "mss_ood_metrics_workspace_bytes": (_sz, [_i64]),
@@ -157,6 +159,10 @@ def forbid_grad(what: str, *tensors):
         raise MssError(f"{what} has no backward kernel: its inputs require grad and autograd is enabled. "
                        "Call it under torch.no_grad() (evaluation), or detach() the inputs; the differentiable "
                        "entry points are deeplab.energy_func / Upsample / anomaly_score.")
+
+
+def wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 
 
 def ptr(t):

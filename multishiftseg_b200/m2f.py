@@ -73,6 +73,47 @@ def _run(cls_logits, mask_logits, padded_size, crop_size, want_semseg, want_anom
     return semseg, anomaly, counts
 
 
+class _AnomalyFn(torch.autograd.Function):
+    """1 - max_c sum_q softmax(cls)[q, c] sigmoid(upsample(masks))[q] with its backward (Mask2Former
+    half): train_m2f.py:443 differentiates through get_anomaly_score (:387-407)."""
+
+    @staticmethod
+    def forward(ctx, cls_logits, mask_logits, Hp, Wp, Hc, Wc, flags):
+        _, anomaly, _ = _run(cls_logits, mask_logits, (Hp, Wp), (Hc, Wc), False, True, False, flags)
+        ctx.save_for_backward(cls_logits, mask_logits)
+        ctx.sizes = (int(Hp), int(Wp), anomaly.shape[-2], anomaly.shape[-1])
+        return anomaly
+
+    @staticmethod
+    def backward(ctx, grad):
+        cls_logits, mask_logits = ctx.saved_tensors
+        Hp, Wp, Hc, Wc = ctx.sizes
+        cls = cls_logits.float().contiguous()
+        masks = mask_logits.float().contiguous()
+        g = grad.float().contiguous()
+        B, Q, C1 = cls.shape
+        h, w = masks.shape[-2:]
+        lib = L.load()
+        gc = torch.empty_like(cls)
+        gm = torch.empty_like(masks)
+        nbytes = lib.mss_m2f_anomaly_backward_workspace_bytes(B, Q, C1 - 1, Hc, Wc)
+        ws = L.workspace(nbytes, cls.device)
+        with torch.cuda.device(cls.device):
+            rc = lib.mss_m2f_anomaly_backward(cls.data_ptr(), masks.data_ptr(), g.data_ptr(), B, Q, C1 - 1, h, w, Hp, Wp, Hc, Wc,
+                                              gc.data_ptr(), gm.data_ptr(), ws.data_ptr(), nbytes, L.stream_ptr(cls.device))
+        L.check(rc, "mss_m2f_anomaly_backward")
+        return gc.to(cls_logits.dtype), gm.to(mask_logits.dtype), None, None, None, None, None
+
+
+def _anomaly(cls_logits, mask_logits, padded_size, size, flags=0):
+    if L.wants_grad(cls_logits, mask_logits):
+        L.require_cuda(cls_logits, "class logits")
+        L.require_cuda(mask_logits, "mask logits")
+        return _AnomalyFn.apply(cls_logits, mask_logits, int(padded_size[0]), int(padded_size[1]), int(size[0]), int(size[1]),
+                                flags)
+    return _run(cls_logits, mask_logits, padded_size, size, False, True, False, flags)[1]
+
+
 def semantic_inference(mask_cls: torch.Tensor, mask_pred: torch.Tensor, num_classes: Optional[int] = None) -> torch.Tensor:
     """maskformer_model.py:341-354 for ONE image: ``mask_cls`` [Q, C+1], ``mask_pred`` [Q, H, W] (already
     upsampled, as the reference passes it) -> [C + K, H, W]."""
@@ -86,14 +127,14 @@ def semantic_inference(mask_cls: torch.Tensor, mask_pred: torch.Tensor, num_clas
 def get_anomaly_score(other_outputs: Dict[str, torch.Tensor], size: Tuple[int, int]) -> torch.Tensor:
     """train_m2f.py:387-407: ``other_outputs["pred_masks_ood"]`` is the already-upsampled [B, Q, Hp, Wp].
 
-    Forward only (evaluation: test_m2f.py:135, valid_batch): the reference also calls this inside the training loop
-    with autograd on (train_m2f.py:443); there is no backward kernel for the fused Mask2Former path (SURVEY 8f rank 4,
-    Mask2Former half), so inputs that require grad raise ``MssError`` instead of returning a tensor without grad_fn."""
+    Differentiable: the reference also calls this inside the training step with autograd on (train_m2f.py:443); with
+    inputs that require grad the result carries a grad_fn backed by ``mss_m2f_anomaly_backward`` (gradients w.r.t.
+    ``pred_logits_ood`` and ``pred_masks_ood``).  The semantic-segmentation outputs (``semantic_inference``,
+    ``post_head_inference``) stay forward-only and raise ``MssError`` for grad-tracked inputs."""
     cls = other_outputs["pred_logits_ood"]
     masks = other_outputs["pred_masks_ood"]
     Hp, Wp = masks.shape[-2:]
-    _, anomaly, _ = _run(cls, masks, (Hp, Wp), size, False, True, False)
-    return anomaly
+    return _anomaly(cls, masks, (Hp, Wp), size)
 
 
 def post_head_inference(pred_logits: torch.Tensor, pred_masks: torch.Tensor, padded_size: Sequence[int],
@@ -119,9 +160,9 @@ def post_head_inference(pred_logits: torch.Tensor, pred_masks: torch.Tensor, pad
 
 def anomaly_score_from_lowres(pred_logits_ood: torch.Tensor, pred_masks_ood: torch.Tensor, padded_size: Sequence[int],
                               size: Sequence[int], flags: int = 0) -> torch.Tensor:
-    """maskformer_model.py:271-277 + train_m2f.py:387-407 fused: [B, Q, h, w] decoder masks -> [B, H, W] score."""
-    _, anomaly, _ = _run(pred_logits_ood, pred_masks_ood, padded_size, size, False, True, False, flags)
-    return anomaly
+    """maskformer_model.py:271-277 + train_m2f.py:387-407 fused: [B, Q, h, w] decoder masks -> [B, H, W] score.
+    Differentiable w.r.t. both inputs (gradient at decoder resolution: the upsample's adjoint is fused in)."""
+    return _anomaly(pred_logits_ood, pred_masks_ood, padded_size, size, flags)
 
 
 def mask_logits(mask_embed: torch.Tensor, mask_features: torch.Tensor) -> torch.Tensor:

@@ -78,3 +78,74 @@ def test_no_grad_paths_unchanged():
         assert not deeplab.energy_func(x).requires_grad
         assert not deeplab.anomaly_score(x, (16, 32)).requires_grad
     assert not deeplab.energy_func(x.detach()).requires_grad
+
+
+# ---- Mask2Former half: backward of the fused anomaly score -------------------------------------------
+def _m2f_ref_grads(cls, lo, padded, crop, g):
+    """torch autograd (CPU, fp32) through the oracle's restatement of maskformer_model.py:271-277 + train_m2f.py:387-407"""
+    from oracle import scoring_oracle as so
+    c = cls.clone().requires_grad_(True)
+    m = lo.clone().requires_grad_(True)
+    a = so.m2f_anomaly_from_lowres(c, m, padded, crop)
+    a.backward(g)
+    return a.detach(), c.grad, m.grad
+
+
+@pytest.mark.parametrize("B,Q,hw,crop", [(1, 100, (16, 32), (64, 128)), (2, 100, (16, 32), (61, 125)), (1, 37, (9, 14), (36, 56)),
+                                         (1, 8, (12, 20), (40, 70))])
+def test_m2f_anomaly_backward_matches_torch_autograd(B, Q, hw, crop):
+    from multishiftseg_b200 import m2f
+    g = torch.Generator().manual_seed(B * 1000 + Q)
+    cls = 3.0 * torch.randn((B, Q, 20), generator=g)
+    lo = 4.0 * torch.randn((B, Q) + hw, generator=g)
+    padded = (4 * hw[0], 4 * hw[1])
+    go = torch.randn((B,) + crop, generator=g)
+    a_ref, gc_ref, gm_ref = _m2f_ref_grads(cls, lo, padded, crop, go)
+    c = cls.cuda().requires_grad_(True)
+    m = lo.cuda().requires_grad_(True)
+    a = m2f.anomaly_score_from_lowres(c, m, padded, crop)
+    np.testing.assert_allclose(a.detach().cpu().numpy(), a_ref.numpy(), rtol=1e-5, atol=2e-6)
+    a.backward(go.cuda())
+    for got, want in ((c.grad, gc_ref), (m.grad, gm_ref)):
+        tol = 1e-5 * float(want.abs().max()) + 1e-7
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=tol)
+
+
+def test_m2f_anomaly_backward_non_x4_resize_and_get_anomaly_score():
+    """generic resize factor (the adjoint is recomputed from the forward's own tap arithmetic) and the reference entry
+    point get_anomaly_score with already-upsampled masks (identity resize)"""
+    from multishiftseg_b200 import m2f
+    from oracle import scoring_oracle as so
+    g = torch.Generator().manual_seed(5)
+    cls = 2.0 * torch.randn((1, 20, 20), generator=g)
+    lo = 3.0 * torch.randn((1, 20, 10, 15), generator=g)
+    go = torch.randn((1, 25, 38), generator=g)
+    a_ref, gc_ref, gm_ref = _m2f_ref_grads(cls, lo, (25, 38), (25, 38), go)
+    c, m = cls.cuda().requires_grad_(True), lo.cuda().requires_grad_(True)
+    m2f.anomaly_score_from_lowres(c, m, (25, 38), (25, 38)).backward(go.cuda())
+    np.testing.assert_allclose(c.grad.cpu().numpy(), gc_ref.numpy(), rtol=1e-4, atol=1e-5 * float(gc_ref.abs().max()))
+    np.testing.assert_allclose(m.grad.cpu().numpy(), gm_ref.numpy(), rtol=1e-4, atol=1e-5 * float(gm_ref.abs().max()))
+    # get_anomaly_score: masks already at full resolution
+    up = 3.0 * torch.randn((1, 20, 24, 40), generator=g)
+    go2 = torch.randn((1, 20, 33), generator=g)
+    cr = cls.clone().requires_grad_(True)
+    ur = up.clone().requires_grad_(True)
+    so.get_anomaly_score({"pred_logits_ood": cr, "pred_masks_ood": ur}, (20, 33)).backward(go2)
+    c2, u2 = cls.cuda().requires_grad_(True), up.cuda().requires_grad_(True)
+    m2f.get_anomaly_score({"pred_logits_ood": c2, "pred_masks_ood": u2}, (20, 33)).backward(go2.cuda())
+    np.testing.assert_allclose(c2.grad.cpu().numpy(), cr.grad.numpy(), rtol=1e-4, atol=1e-5 * float(cr.grad.abs().max()))
+    np.testing.assert_allclose(u2.grad.cpu().numpy(), ur.grad.numpy(), rtol=1e-4, atol=1e-5 * float(ur.grad.abs().max()))
+
+
+def test_m2f_anomaly_backward_is_deterministic():
+    from multishiftseg_b200 import m2f
+    g = torch.Generator().manual_seed(9)
+    cls = (3.0 * torch.randn((2, 100, 20), generator=g)).cuda()
+    lo = (4.0 * torch.randn((2, 100, 32, 64), generator=g)).cuda()
+    go = torch.randn((2, 128, 256), generator=g).cuda()
+    outs = []
+    for _ in range(2):
+        c, m = cls.clone().requires_grad_(True), lo.clone().requires_grad_(True)
+        m2f.anomaly_score_from_lowres(c, m, (128, 256), (128, 256)).backward(go)
+        outs.append((c.grad.clone(), m.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

@@ -147,14 +147,18 @@ def test_forward_only_ops_refuse_grad_inputs_on_gpu():
     cls = torch.randn((1, 100, 20), device="cuda", requires_grad=True)
     lo = torch.randn((1, 100, 8, 16), device="cuda")
     with pytest.raises(_lib.MssError):
-        m2f.anomaly_score_from_lowres(cls, lo, (32, 64), (32, 64))
+        m2f.post_head_inference(cls, lo, (32, 64))
     with pytest.raises(_lib.MssError):
-        m2f.get_anomaly_score({"pred_logits_ood": cls, "pred_masks_ood": torch.randn((1, 100, 32, 64), device="cuda")}, (32, 64))
+        m2f.semantic_inference(cls[0], torch.randn((100, 32, 64), device="cuda"))
+    with pytest.raises(_lib.MssError):
+        m2f.mask_logits(torch.randn((1, 100, 32), device="cuda", requires_grad=True), torch.randn((1, 32, 8, 16), device="cuda"))
     with pytest.raises(_lib.MssError):
         deeplab.score_maps(torch.randn((1, 19, 8, 8), device="cuda", requires_grad=True), ("msp",))
     with torch.no_grad():
-        m2f.anomaly_score_from_lowres(cls, lo, (32, 64), (32, 64))
+        m2f.post_head_inference(cls, lo, (32, 64))
     # the differentiable entry points keep working
     x = torch.randn((1, 19, 8, 8), device="cuda", requires_grad=True)
     deeplab.energy_func(x).sum().backward()
     assert x.grad is not None and bool(torch.isfinite(x.grad).all())
+    a = m2f.anomaly_score_from_lowres(cls, lo, (32, 64), (32, 64))
+    assert a.grad_fn is not None
