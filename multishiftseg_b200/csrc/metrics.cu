@@ -234,7 +234,9 @@ __device__ __forceinline__ long long load_T(const unsigned long long *d_T, long 
 // totals_out[0] = number of kept points (written by the last tile); tile_best[tile] = FPR95 candidate of the tile.
 constexpr int RC_THREADS = 256;
 constexpr int RC_IPT = 4;
-constexpr int RC_SUB = 16;
+constexpr int RC_SUB = 16;                                // layout bound of the (sub-tile, warp) tables: 16 x 8 = 32 lanes x 4
+constexpr int RC_SUB_USED = 8;                            // tiles of 8192 thresholds: with 16 sub-tiles the re-read of phase B came
+                                                          // from DRAM (ncu: 2.0 GB read for 1.05 GB of input)
 constexpr int RC_SUBTILE = RC_THREADS * RC_IPT;           // 1024 thresholds
 constexpr int CT_TILE_MAX = RC_SUBTILE * RC_SUB;          // 16384 thresholds per ROC / FPR95 tile at most
 
@@ -891,7 +893,7 @@ static int tail1_enqueue(const int64_t *tps_, const int64_t *fps_, const unsigne
     if (w.tiles_upper == 0) return MSS_OK;
     // sub-tiles per tile: fat tiles for big inputs (one look-back per 16384 thresholds), >= ~4 tiles per SM for small ones
     const long long T_upper = d_T ? (long long)w.tiles_upper * RC_SUBTILE : (long long)T_host;
-    const int sub = (int)std::max<long long>(1, std::min<long long>(RC_SUB, T_upper / ((long long)RC_SUBTILE * 4 * sm_count())));
+    const int sub = (int)std::max<long long>(1, std::min<long long>(RC_SUB_USED, T_upper / ((long long)RC_SUBTILE * 4 * sm_count())));
     const long long tile_thr = (long long)sub * RC_SUBTILE;
     const unsigned tiles = (unsigned)((T_upper + tile_thr - 1) / tile_thr);
     roc_compact_kernel<<<tiles, RC_THREADS + 32, 0, st>>>(tps, fps, d_T, T_host, sub, recall_level, w.status, w.counter,
