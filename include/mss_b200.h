@@ -298,13 +298,18 @@ MSS_API int mss_eval_partition_scatter(const mss_eval_buffers *ev, int64_t n_neg
 MSS_API int mss_eval_exchange_append(const mss_eval_buffers *ev, int64_t n_neg, int64_t n_pos, const uint32_t *splitters_host,
                              int parts, const uint64_t *dst_keys_host, const uint64_t *dst_state_host,
                              int64_t dst_capacity, void *workspace, size_t workspace_bytes, void *stream);
-/* Streaming form of the same exchange: ENQUEUES (no host synchronisation) the remote append of a STAGING evaluator --
- * its stream sizes are read from its device state, so a batch can be exchanged right behind the kernel that scored it
- * while the next batch is scored on another stream -- followed by `accum_state += staging state; staging state = 0`.
- * splitters_dev is a DEVICE array [parts - 1]; accum_state MSS_EVAL_STATE_BYTES device bytes. */
+/* Streaming form of the same exchange: ENQUEUES (no host synchronisation) the exchange of a STAGING evaluator -- its
+ * stream sizes are read from its device state, so a batch can be exchanged right behind the kernel that scored it while
+ * the next batch is scored on another stream -- followed by `accum_state += staging state; staging state = 0`.
+ * splitters_dev is a DEVICE array [parts - 1]; accum_state MSS_EVAL_STATE_BYTES device bytes.
+ * workspace == NULL: every tile reserves its runs itself (one remote atomic per tile and destination);
+ * workspace of mss_eval_exchange_stream_workspace_bytes(staging capacity, parts) bytes and parts <= 16: the batch is
+ * counted per destination, ONE run per destination and stream is reserved remotely, and the keys are scattered with a
+ * look-back between tiles (2 x parts remote atomics per batch). */
+MSS_API size_t mss_eval_exchange_stream_workspace_bytes(int64_t staging_capacity, int parts);
 MSS_API int mss_eval_exchange_stream(const mss_eval_buffers *staging, const uint32_t *splitters_dev, int parts,
                              const uint64_t *dst_keys_host, const uint64_t *dst_state_host, int64_t dst_capacity,
-                             void *accum_state, void *stream);
+                             void *accum_state, void *workspace, size_t workspace_bytes, void *stream);
 /* two sorted key arrays (negatives = in-distribution, positives = OOD) -> per distinct key of their union the
  * cumulative counts  tps[k] = pos_before + #{positives with key <= key_k},  fps[k] = neg_before + #{negatives with
  * key <= key_k}  (int64; one merge-path pass).  tps/fps need room for n_neg + n_pos entries.  *T_host = number of

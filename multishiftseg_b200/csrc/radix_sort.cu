@@ -726,7 +726,8 @@ __device__ __forceinline__ void partition_tile_bulk(PartSmem &sm, const uint32_t
     __syncthreads();
     // one thread per destination: <= 3 head keys, one bulk copy, <= 3 tail keys
     if ((int)tid < nd) {
-        const unsigned cnt = sm.count[tid], st0 = sm.start[tid];
+        // (a zero table entry = the destination refused the reservation: its run is dropped, the owner reports the overflow)
+        const unsigned cnt = __ldg(table + tid) ? sm.count[tid] : 0u, st0 = sm.start[tid];
         const unsigned long long a = sm.dst[tid];
         const unsigned head = min(cnt, (unsigned)(((16ull - (a & 15ull)) & 15ull) >> 2));
         const unsigned body = (cnt - head) & ~3u;
@@ -925,6 +926,92 @@ __global__ void eval_state_fold_kernel(EvalState *accum, EvalState *staging) {
     accum->inf_flag |= staging->inf_flag;
     accum->overflow += staging->overflow;
     staging->n_neg = 0; staging->n_pos = 0; staging->nan_flag = 0; staging->inf_flag = 0; staging->overflow = 0;
+}
+
+// ---- streamed exchange without per-tile remote atomics ------------------------------------------------------
+// One batch (a staging evaluator whose sizes live in its device state): count its keys per destination, reserve ONE run
+// per destination and stream with a system-scope atomicAdd (2 x ranks remote atomics per batch instead of one per tile
+// and destination), then the look-back / bulk-store scatter at the reserved addresses.  No host involvement.
+struct StagingView {
+    const uint32_t *keys;
+    long long capacity;
+    const EvalState *state;
+    __device__ __forceinline__ void stream(int positives, const uint32_t *&p, long long &n) const {
+        const long long n_neg = (long long)min(state->n_neg, (unsigned long long)capacity);
+        const long long n_pos = (long long)min(state->n_pos, (unsigned long long)(capacity - n_neg));
+        p = positives ? keys + (capacity - n_pos) : keys;
+        n = positives ? n_pos : n_neg;
+    }
+};
+
+// blockIdx.y = stream; counts[stream][RADIX]; parts <= 16 (lane-private counters)
+__global__ void __launch_bounds__(256)
+partition_count_dev_kernel(StagingView sv, const uint32_t *__restrict__ splitters, int nspl, int steps,
+                           unsigned long long *__restrict__ counts_all) {
+    __shared__ unsigned s_c[PB_MAX_PARTS * 256];
+    __shared__ uint32_t s_spl[PB_MAX_PARTS];
+    const uint32_t *keys;
+    long long n;
+    sv.stream(blockIdx.y, keys, n);
+    unsigned long long *counts = counts_all + blockIdx.y * RADIX;
+    for (int i = threadIdx.x; i < PB_MAX_PARTS * 256; i += 256) s_c[i] = 0;
+    if ((int)threadIdx.x < nspl) s_spl[threadIdx.x] = __ldg(splitters + threadIdx.x);
+    __syncthreads();
+    const SplitterDigit dg{s_spl, nspl, steps};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s_c[dg(__ldg(keys + i)) * 256 + threadIdx.x]++;
+    __syncthreads();
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = warp; p <= nspl; p += 8) {
+        unsigned long long acc = 0;
+        for (int t = lane; t < 256; t += 32) acc += s_c[p * 256 + t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && acc) atomicAdd(counts + p, acc);
+    }
+}
+
+// thread (stream, destination): reserve the batch's run, write its byte address (0 = refused) into table[stream][d]
+__global__ void exchange_reserve_kernel(const unsigned long long *__restrict__ counts_all, ExchangeDst dst, int parts,
+                                        unsigned long long *__restrict__ table_all) {
+    const int sid = threadIdx.x / PB_MAX_PARTS, d = threadIdx.x % PB_MAX_PARTS;
+    if (sid > 1 || d >= parts) return;
+    const unsigned long long tot = counts_all[sid * RADIX + d];
+    unsigned long long addr = dst.keys[d];                 // (an empty run still needs a non-zero entry)
+    if (tot) {
+        EvalState *es = reinterpret_cast<EvalState *>(dst.state[d]);
+        const unsigned long long base = atomicAdd_system(sid ? &es->n_pos : &es->n_neg, tot);
+        if (base + tot > (unsigned long long)dst.capacity) {
+            atomicAdd_system(&es->overflow, tot);
+            addr = 0;
+        } else {
+            addr = dst.keys[d] + 4ull * (sid ? (unsigned long long)dst.capacity - base - tot : base);
+        }
+    }
+    table_all[sid * PB_MAX_PARTS + d] = addr;
+}
+
+// blockIdx.y = stream; tickets, status words and the address table per stream
+__global__ void __launch_bounds__(SORT_THREADS, 4)
+partition_scatter_bulk_dev_kernel(StagingView sv, const uint32_t *__restrict__ splitters, int nspl, int steps,
+                                  const unsigned long long *__restrict__ table_all, unsigned long long *status_all,
+                                  size_t status_words, int sstride, unsigned *counters) {
+    __shared__ PartSmem sm;
+    const unsigned tid = threadIdx.x;
+    const uint32_t *keys;
+    long long n;
+    sv.stream(blockIdx.y, keys, n);
+    if (tid == 0) sm.tile = atomicAdd(counters + blockIdx.y, 1u);
+    if (tid < SORT_WARPS * PB_MAX_PARTS) (&sm.warp_hist[0][0])[tid] = 0;
+    if ((int)tid < nspl) sm.spl[tid] = __ldg(splitters + tid);
+    __syncthreads();
+    if ((long long)sm.tile * SORT_TILE >= n) return;       // tickets beyond the batch (the grid is sized for the capacity)
+    const unsigned long long *table = table_all + blockIdx.y * PB_MAX_PARTS;
+    unsigned long long *status = status_all + blockIdx.y * status_words;
+    if ((long long)(sm.tile + 1) * SORT_TILE <= n)
+        partition_tile_bulk<true>(sm, keys, n, table, status, sstride, nspl + 1, steps);
+    else
+        partition_tile_bulk<false>(sm, keys, n, table, status, sstride, nspl + 1, steps);
 }
 
 // top-`bits` histogram for splitter selection (bins = 1 << bits <= 65536).
@@ -1471,9 +1558,18 @@ extern "C" int mss_eval_exchange_append(const mss_eval_buffers *ev, int64_t n_ne
 
 // Streaming form: enqueue (no host synchronisation) the exchange of a STAGING evaluator -- its sizes are read from its
 // device state -- followed by `accum_state += staging state; staging state = 0`.  splitters_dev is a DEVICE array.
+// With a workspace (mss_eval_exchange_stream_workspace_bytes) and parts <= 16 the counted form runs: per-destination
+// counts of the batch, ONE remote reservation per destination and stream, look-back / bulk-store scatter; without one,
+// every tile reserves its own runs (exchange_append_dev_kernel).
+extern "C" size_t mss_eval_exchange_stream_workspace_bytes(int64_t staging_capacity, int parts) {
+    if (staging_capacity < 0) staging_capacity = 0;
+    const size_t tiles = sort_tiles(staging_capacity) + 2;
+    return 2 * RADIX * 8 + 2 * PB_MAX_PARTS * 8 + 256 + 2 * tiles * (size_t)status_stride(parts) * 8 + 2048;
+}
+
 extern "C" int mss_eval_exchange_stream(const mss_eval_buffers *staging, const uint32_t *splitters_dev, int parts,
                                         const uint64_t *dst_keys_host, const uint64_t *dst_state_host, int64_t dst_capacity,
-                                        void *accum_state, void *stream) {
+                                        void *accum_state, void *workspace, size_t workspace_bytes, void *stream) {
     MSS_REQUIRE(parts >= 1 && parts <= PB_MAX_PARTS, "mss_eval_exchange_stream: parts must be 1..%d", PB_MAX_PARTS);
     MSS_REQUIRE(staging && staging->keys && staging->state && staging->capacity > 0 && accum_state && dst_keys_host &&
                     dst_state_host && dst_capacity > 0 && (parts == 1 || splitters_dev),
@@ -1490,10 +1586,36 @@ extern "C" int mss_eval_exchange_stream(const mss_eval_buffers *staging, const u
     cudaStream_t st = (cudaStream_t)stream;
     const size_t tiles = sort_tiles(staging->capacity) + 2;            // two streams: up to one partial tile each
     MSS_REQUIRE(tiles < (1ull << 31), "mss_eval_exchange_stream: staging buffer too large");
-    exchange_append_dev_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(staging->keys, staging->capacity,
-                                                                        (const EvalState *)staging->state, splitters_dev,
-                                                                        parts - 1, splitter_steps(parts), dst);
-    MSS_CHECK_LAUNCH();
+    const int steps = splitter_steps(parts);
+    if (workspace && parts <= 16) {
+        if (workspace_bytes < mss_eval_exchange_stream_workspace_bytes(staging->capacity, parts)) {
+            set_error("mss_eval_exchange_stream: workspace too small (%zu < %zu)", workspace_bytes,
+                      mss_eval_exchange_stream_workspace_bytes(staging->capacity, parts));
+            return MSS_ERR_WORKSPACE;
+        }
+        const int sstride = status_stride(parts);
+        Carver c(workspace, workspace_bytes);
+        unsigned long long *counts = c.take<unsigned long long>(2 * RADIX);
+        unsigned long long *table = c.take<unsigned long long>(2 * PB_MAX_PARTS);
+        unsigned *counters = c.take<unsigned>(64);
+        unsigned long long *status = c.take<unsigned long long>(2 * tiles * sstride);
+        MSS_REQUIRE(c.ok(), "mss_eval_exchange_stream: internal workspace layout");
+        MSS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)((char *)(status + 2 * tiles * sstride) - (char *)workspace), st));
+        const StagingView sv{staging->keys, staging->capacity, (const EvalState *)staging->state};
+        const int cgrid = (int)std::max<long long>(1, std::min<long long>((staging->capacity + 4095) / 4096, (long long)sm_count() * 4));
+        partition_count_dev_kernel<<<dim3(cgrid, 2), 256, 0, st>>>(sv, splitters_dev, parts - 1, steps, counts);
+        MSS_CHECK_LAUNCH();
+        exchange_reserve_kernel<<<1, 2 * PB_MAX_PARTS, 0, st>>>(counts, dst, parts, table);
+        MSS_CHECK_LAUNCH();
+        partition_scatter_bulk_dev_kernel<<<dim3((unsigned)tiles, 2), SORT_THREADS, 0, st>>>(sv, splitters_dev, parts - 1, steps, table,
+                                                                                           status, tiles * sstride, sstride, counters);
+        MSS_CHECK_LAUNCH();
+    } else {
+        exchange_append_dev_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(staging->keys, staging->capacity,
+                                                                            (const EvalState *)staging->state, splitters_dev,
+                                                                            parts - 1, steps, dst);
+        MSS_CHECK_LAUNCH();
+    }
     eval_state_fold_kernel<<<1, 1, 0, st>>>((EvalState *)accum_state, (EvalState *)staging->state);
     MSS_CHECK_LAUNCH();
     return MSS_OK;
