@@ -97,6 +97,56 @@ static void choose_splitters(const long long *hist, int bins_log2, int world, st
     }
 }
 
+// Bins a splitter would have to fall INSIDE of: the bin in front of a chosen boundary when it holds more than half of one
+// rank's share (evaluator.heavy_bins).
+static std::vector<int> heavy_bins(const long long *hist, int bins_log2, int world, const std::vector<uint32_t> &spl) {
+    const int bins = 1 << bins_log2;
+    long long total = 0;
+    for (int b = 0; b < bins; b++) total += hist[b];
+    const long long share = std::max<long long>(total / std::max(world, 1), 1);
+    std::vector<int> out;
+    for (uint32_t s : spl) {
+        const int b = (int)std::min<long long>((long long)(s >> (32 - bins_log2)), bins) - 1;
+        if (b >= 0 && b < bins && hist[b] * 2 > share && std::find(out.begin(), out.end(), b) == out.end()) out.push_back(b);
+    }
+    std::sort(out.begin(), out.end());
+    return out;
+}
+
+// Splitters with a second level inside the heavy bins (evaluator.refine_splitters, same integer arithmetic).
+// fine[i * 65536 ...] = global histogram of the low 16 key bits inside heavy[i].
+static void refine_splitters(const long long *hist, int world, const std::vector<int> &heavy, const std::vector<long long> &fine,
+                             std::vector<uint32_t> &out) {
+    const int bins = 1 << 16;
+    long long total = 0;
+    for (int b = 0; b < bins; b++) total += hist[b];
+    out.clear();
+    long long cum = 0;                                                     // keys in bins < b
+    int b = 0;
+    for (int j = 1; j < world; j++) {
+        const long long target = (total * j + world - 1) / world;
+        while (b < bins - 1 && cum + hist[b] < target) cum += hist[b++];
+        unsigned long long key = (unsigned long long)(b + 1) << 16;
+        const auto it = std::find(heavy.begin(), heavy.end(), b);
+        if (it != heavy.end()) {
+            const long long *f = fine.data() + (size_t)(it - heavy.begin()) * bins;
+            long long tot_f = 0;
+            for (int i = 0; i < bins; i++) tot_f += f[i];
+            if (tot_f > 0) {
+                const long long inside = target - cum, hb = std::max<long long>(hist[b], 1);
+                const long long want = std::max<long long>((inside * tot_f + hist[b] - 1) / hb, 1);
+                long long fc = 0;
+                int i = 0;
+                while (i < bins && fc + f[i] < want) fc += f[i++];         // first low value whose cumulative count reaches want
+                key = ((unsigned long long)b << 16) + (unsigned long long)std::min(i + 1, bins);
+            }
+        }
+        uint32_t k32 = (uint32_t)std::min<unsigned long long>(key, 0xFFFFFFFFull);
+        if (!out.empty()) k32 = std::max(k32, out.back());
+        out.push_back(k32);
+    }
+}
+
 }  // namespace mss
 
 using namespace mss;
@@ -147,6 +197,22 @@ extern "C" int mss_ood_metrics_dist(const mss_eval_buffers *ev, void *nccl_comm,
     for (int b = 0; b < (1 << BITS); b++) h_hist[b] += h_hist[(1 << BITS) + b];
     std::vector<uint32_t> spl;
     choose_splitters(h_hist.data(), BITS, world, spl);
+    // saturated / narrow-range scores: second-level histogram inside the bins a splitter should cut through
+    const std::vector<int> heavy = heavy_bins(h_hist.data(), BITS, world, spl);
+    if (!heavy.empty()) {
+        std::vector<long long> fine(heavy.size() << BITS), h2((size_t)2 << BITS);
+        for (size_t i = 0; i < heavy.size(); i++) {
+            rc = mss_keys_histogram_refine(neg, n_neg, (unsigned)heavy[i], every, (int64_t *)d_hist, stream);
+            if (rc) return rc;
+            rc = mss_keys_histogram_refine(pos, n_pos, (unsigned)heavy[i], every, (int64_t *)d_hist + (1 << BITS), stream);
+            if (rc) return rc;
+            MSS_CHECK_NCCL(nc.all_reduce(d_hist, d_hist, (size_t)2 << BITS, NCCL_INT64, NCCL_SUM, nccl_comm, st));
+            MSS_CHECK_CUDA(cudaMemcpyAsync(h2.data(), d_hist, h2.size() * 8, cudaMemcpyDeviceToHost, st));
+            MSS_CHECK_CUDA(cudaStreamSynchronize(st));
+            for (int b = 0; b < (1 << BITS); b++) fine[(i << BITS) + b] = h2[b] + h2[(1 << BITS) + b];
+        }
+        refine_splitters(h_hist.data(), world, heavy, fine, spl);
+    }
     uint32_t *d_spl = tmp.get<uint32_t>(world);
     MSS_REQUIRE(d_spl, "mss_ood_metrics_dist: cudaMallocAsync failed");
     if (world > 1) MSS_CHECK_CUDA(cudaMemcpyAsync(d_spl, spl.data(), (size_t)(world - 1) * 4, cudaMemcpyHostToDevice, st));

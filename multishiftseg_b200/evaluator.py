@@ -83,6 +83,14 @@ class CudaBackend:
                                                         L.stream_ptr(self.device)), "mss_keys_histogram_sampled")
         return hist
 
+    def histogram_refine(self, keys: torch.Tensor, m: int, prefix16: int, every: int = 1) -> torch.Tensor:
+        """Second level: histogram of the LOW 16 key bits of the keys whose top 16 bits equal ``prefix16`` (same sampling)."""
+        hist = torch.empty(1 << 16, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.load().mss_keys_histogram_refine(keys.data_ptr(), m, int(prefix16), int(every), hist.data_ptr(),
+                                                       L.stream_ptr(self.device)), "mss_keys_histogram_refine")
+        return hist
+
     def partition(self, keys, m: int, splitters: Sequence[int], parts: int):
         import ctypes as C
         lib = L.load()
@@ -247,6 +255,75 @@ def choose_splitters(hist: np.ndarray, world: int, bits: int = HIST_BITS) -> Lis
     return out
 
 
+def heavy_bins(hist: np.ndarray, splitters: Sequence[int], world: int, bits: int = HIST_BITS) -> List[int]:
+    """Top-``bits`` bins in which a splitter should fall but cannot at bin granularity: the bin right before a splitter's
+    boundary when it holds more than half of one rank's share (saturated or narrow-range scores).  Ascending, unique."""
+    hist = np.asarray(hist, dtype=np.int64)
+    share = max(int(hist.sum()) // max(world, 1), 1)
+    out = []
+    for s in splitters:
+        b = min(s >> (32 - bits), 1 << bits) - 1
+        if 0 <= b < (1 << bits) and int(hist[b]) * 2 > share and b not in out:
+            out.append(int(b))
+    return sorted(out)
+
+
+def refine_splitters(hist: np.ndarray, fine: dict, world: int, bits: int = HIST_BITS) -> List[int]:
+    """Splitters with a second level inside the heavy bins: ``fine[b]`` is the GLOBAL histogram of the low 32 - bits key
+    bits inside top bin ``b``.  Same integer arithmetic on identical inputs on every rank => identical splitters."""
+    hist = np.asarray(hist, dtype=np.int64)
+    total = int(hist.sum())
+    cum = np.cumsum(hist)
+    low_bits = 32 - bits
+    out: List[int] = []
+    for j in range(1, world):
+        target = (total * j + world - 1) // world
+        b = int(np.searchsorted(cum, target, side="left"))                 # the bin in which the cumulative count reaches target
+        b = min(b, (1 << bits) - 1)
+        if b in fine:
+            before = int(cum[b] - hist[b])
+            fc = np.cumsum(np.asarray(fine[b], dtype=np.int64))
+            # the sampled fine histogram may not add up to hist[b] exactly: scale the remaining target into it
+            inside = target - before
+            tot_f = int(fc[-1])
+            if tot_f > 0:
+                want = (inside * tot_f + int(hist[b]) - 1) // max(int(hist[b]), 1)
+                f = int(np.searchsorted(fc, max(want, 1), side="left")) + 1
+                key = (b << low_bits) + min(f, 1 << low_bits)
+            else:
+                key = (b + 1) << low_bits
+        else:
+            key = (b + 1) << low_bits
+        out.append(min(key, 0xFFFFFFFF))
+    # keep them ascending (a refined splitter can never pass the next bin boundary, but two may coincide)
+    for j in range(1, len(out)):
+        out[j] = max(out[j], out[j - 1])
+    return out
+
+
+def range_estimates(hist: np.ndarray, fine: dict, splitters: Sequence[int], bits: int = HIST_BITS) -> List[int]:
+    """Expected (sampled) number of keys in each splitter range, from the two-level histogram; an upper estimate where a
+    splitter falls inside a bin that has no second level."""
+    hist = np.asarray(hist, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(hist)])
+    low_bits = 32 - bits
+
+    def below(key: int) -> int:                                             # keys < key
+        if key >= 1 << 32:
+            return int(cum[-1])
+        b, low = key >> low_bits, key & ((1 << low_bits) - 1)
+        if low == 0:
+            return int(cum[b])
+        if b in fine:
+            f = np.asarray(fine[b], dtype=np.int64)
+            tot = int(f.sum())
+            return int(cum[b]) + (int(f[:low].sum()) * int(hist[b]) + max(tot, 1) - 1) // max(tot, 1)
+        return int(cum[b + 1])
+
+    edges = [0] + [below(int(s)) for s in splitters] + [int(cum[-1])]
+    return [max(b - a, 0) for a, b in zip(edges[:-1], edges[1:])]
+
+
 class StreamingEvaluator:
     """Accumulate (score, label) batches on the device; compute exact AUROC / AP / FPR@95 at the end.
 
@@ -339,6 +416,30 @@ class StreamingEvaluator:
             torch.cuda.current_stream(be.device).wait_event(st["done"][b])
         return b, st["staging"][b]
 
+    def _pick_splitters(self, hist, neg, n_neg, pos, n_pos, every, world):
+        """Collective.  ``hist``: the all-reduced top-16-bit histogram.  -> (splitters, hist as numpy, {heavy bin: its
+        global low-16-bit histogram}).  A splitter that would have to fall INSIDE a heavy bin (saturated or narrow-range
+        scores) gets a second-level histogram of that bin, so that one rank does not end up owning -- and buffering -- the
+        whole dataset; ties of one exact score still go to one rank, as the algorithm needs."""
+        import torch.distributed as dist
+        be, g = self.backend, self.group
+        hist_np = hist.cpu().numpy()
+        splitters = choose_splitters(hist_np, world)
+        heavy = heavy_bins(hist_np, splitters, world) if hasattr(be, "histogram_refine") else []
+        fine_by_bin: dict = {}
+        if heavy:
+            fine = be.empty(len(heavy) << 16, torch.int64)
+            for i, b in enumerate(heavy):
+                fb = be.histogram_refine(neg, n_neg, b, every)
+                if n_pos:
+                    fb = fb + be.histogram_refine(pos, n_pos, b, every)
+                fine[i << 16: (i + 1) << 16] = fb
+            dist.all_reduce(fine, group=g)
+            fine_np = fine.cpu().numpy()
+            fine_by_bin = {b: fine_np[i << 16: (i + 1) << 16] for i, b in enumerate(heavy)}
+            splitters = refine_splitters(hist_np, fine_by_bin, world)
+        return splitters, hist_np, fine_by_bin
+
     def _stream_calibrate(self, buf):
         """Collective, once: key ranges from the first batch, receive buffers, everything emptied behind a barrier."""
         import torch.distributed as dist
@@ -354,7 +455,7 @@ class StreamingEvaluator:
         if n_pos:
             hist = hist + be.histogram(pos, n_pos, HIST_BITS, every)
         dist.all_reduce(hist, group=g)
-        splitters = choose_splitters(hist.cpu().numpy(), world)
+        splitters, _, _ = self._pick_splitters(hist, neg, m - n_pos, pos, n_pos, every, world)
         need = total_cap // world + total_cap // (4 * world) + (1 << 20)
         self._stream_tag = getattr(self, "_stream_tag", None) or StreamingEvaluator._next_tag()
         pb = self._peer_buffers(need, g, tag=self._stream_tag)
@@ -527,7 +628,8 @@ class StreamingEvaluator:
         if n_pos:
             hist = hist + be.histogram(pos, n_pos, HIST_BITS, every)
         dist.all_reduce(hist, group=g)
-        splitters = choose_splitters(hist.cpu().numpy(), world)
+        splitters, hist_np, fine_by_bin = self._pick_splitters(hist, neg, n_neg, pos, n_pos, every, world)
+        heavy = sorted(fine_by_bin)
         mark("histogram_splitters")
 
         # 3. exchange by key range.  Receive layout on rank r = the evaluator's own two-stream layout.
@@ -541,9 +643,7 @@ class StreamingEvaluator:
         if exchange == "p2p":
             # 3a. remote append: nothing is counted beforehand.  The receive capacity comes from the (sampled) global
             #     histogram: expected keys of the fullest key range + 8 % + 64 K.
-            hn = hist.cpu().numpy().astype(np.int64)
-            bounds = [0] + [min(s >> (32 - HIST_BITS), 1 << HIST_BITS) for s in splitters] + [1 << HIST_BITS]
-            est = max(int(hn[a:b].sum()) for a, b in zip(bounds[:-1], bounds[1:])) * every
+            est = max(range_estimates(hist_np, fine_by_bin, splitters)) * every
             need = est + est // 12 + (1 << 16)
             pb = self._peer_buffers(need, g)
             if pb is None:
@@ -624,7 +724,8 @@ class StreamingEvaluator:
 
         return self._sort_count_tail(r_neg, m2_neg, r_pos, m2_pos, per_dst, recall_level, marks, mark,
                                      {"send_counts": send, "recv_counts": [recv_neg, recv_pos], "splitters": splitters,
-                                      "exchange": exchange})
+                                      "exchange": exchange, "refined_bins": heavy,
+                                      "dst_totals": [int(a) + int(b) for a, b in zip(per_dst[0], per_dst[1])]})
 
     def _sort_count_tail(self, r_neg, m2_neg, r_pos, m2_pos, per_dst, recall_level, marks, mark, info):
         import torch.distributed as dist

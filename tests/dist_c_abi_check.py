@@ -45,9 +45,16 @@ def main():
     lib = L.load()
     ok = True
     cases = [("cont", 2_000_003, 0.05, 0.05), ("q2", 1_000_000, 0.05, 0.2), ("f16", 3_000_001, 0.01, 0.05),
-             ("const", 50_000, 0.3, 0.0), ("cont", 1000, 0.2, 0.0), ("onlyid", 5000, 0.0, 0.1)]
+             ("const", 50_000, 0.3, 0.0), ("cont", 1000, 0.2, 0.0), ("onlyid", 5000, 0.0, 0.1),
+             ("narrow", 2_000_000, 0.05, 0.05)]
     for ci, (mode, n, p_ood, p_ign) in enumerate(cases):
-        s, l = gi.metric_case(600 + ci, n, "cont" if mode == "onlyid" else mode, max(p_ood, 0.01), p_ign, label_dtype="uint8")
+        if mode == "narrow":      # all scores in one top-16-bit key bin: the second-level histogram must split it
+            rng = np.random.default_rng(600 + ci)
+            s = (0.999 + 0.001 * rng.random(n)).astype(np.float32)
+            r = rng.random(n)
+            l = np.where(r < p_ood, 1, np.where(r > 1 - p_ign, 255, 0)).astype(np.uint8)
+        else:
+            s, l = gi.metric_case(600 + ci, n, "cont" if mode == "onlyid" else mode, max(p_ood, 0.01), p_ign, label_dtype="uint8")
         if mode == "onlyid":
             l[l == 1] = 0
         want = c_oracle.eval_ood_measure(s, l)

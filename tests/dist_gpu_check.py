@@ -16,6 +16,17 @@ from multishiftseg_b200.evaluator import StreamingEvaluator  # noqa: E402
 from oracle import c_oracle  # noqa: E402
 
 
+def make_case(seed, n, mode, p_ood, p_ign):
+    if mode != "narrow":
+        return gi.metric_case(seed, n, mode, p_ood, p_ign, label_dtype="uint8")
+    # every score inside ONE top-16-bit key bin (0.999 .. 1.0): bin-granular splitters would send everything to one rank
+    rng = np.random.default_rng(seed)
+    s = (0.999 + 0.001 * rng.random(n)).astype(np.float32)
+    r = rng.random(n)
+    l = np.where(r < p_ood, 1, np.where(r > 1 - p_ign, 255, 0)).astype(np.uint8)
+    return s, l
+
+
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -23,9 +34,10 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
     cases = [("cont", 2_000_003, 0.05, 0.05), ("q2", 1_000_000, 0.05, 0.2), ("f16", 3_000_001, 0.01, 0.05),
-             ("const", 50_000, 0.3, 0.0), ("zeros", 90_000, 0.3, 0.05), ("cont", 1000, 0.2, 0.0)]
+             ("const", 50_000, 0.3, 0.0), ("zeros", 90_000, 0.3, 0.05), ("cont", 1000, 0.2, 0.0),
+             ("narrow", 2_000_000, 0.05, 0.05)]
     for ci, (mode, n, p_ood, p_ign) in enumerate(cases):
-        s, l = gi.metric_case(500 + ci, n, mode, p_ood, p_ign, label_dtype="uint8")
+        s, l = make_case(500 + ci, n, mode, p_ood, p_ign)
         img = max(n // 16, 1)
         chunks = [(i, min(i + img, n)) for i in range(0, n, img)]
         want = c_oracle.eval_ood_measure(s, l)
@@ -38,11 +50,14 @@ def main():
             got = ev.compute()
             got = None if got is None else tuple(float(v) for v in got)
             good = (got == want == one)
+            if good and mode == "narrow" and world > 1:        # the second-level histogram must have balanced the key ranges
+                rc = ev.last_exchange.get("dst_totals")
+                good = bool(ev.last_exchange.get("refined_bins")) and max(rc) <= 1.25 * (sum(rc) / world) + 4096
             ok &= good
             if rank == 0:
-                x = ev.last_exchange if good and got else {}
+                x = ev.last_exchange if got else {}
                 print(f"[world {world}] {mode:6s} n={n:8d} {exch:11s}->{x.get('exchange')} multi-gpu == 1-gpu == oracle: {good}  {got}  "
-                      f"recv={x.get('recv_counts', '')} {x.get('p2p_error') or ''}", flush=True)
+                      f"dst_totals={x.get('dst_totals', '')} {x.get('p2p_error') or ''}", flush=True)
     # streaming exchange: every batch goes to its owners right behind its append (key ranges fixed from the first batch)
     for ci, (mode, n, p_ood, p_ign) in enumerate(cases[:4]):
         s, l = gi.metric_case(500 + ci, n, mode, p_ood, p_ign, label_dtype="uint8")

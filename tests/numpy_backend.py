@@ -71,6 +71,13 @@ class NumpyBackend:
             k = k[: m - m % 4].reshape(-1, 4)[::every].reshape(-1)
         return torch.from_numpy(np.bincount(k >> np.uint32(32 - bits), minlength=1 << bits).astype(np.int64))
 
+    def histogram_refine(self, keys, m, prefix16, every=1):
+        k = _u32(keys, m)
+        if every > 1:
+            k = k[: m - m % 4].reshape(-1, 4)[::every].reshape(-1)
+        k = k[(k >> np.uint32(16)) == np.uint32(prefix16)]
+        return torch.from_numpy(np.bincount(k & np.uint32(0xFFFF), minlength=1 << 16).astype(np.int64))
+
     def partition(self, keys, m, splitters, parts):
         k = _u32(keys, m)
         dest = np.searchsorted(np.asarray(splitters, dtype=np.uint64), k.astype(np.uint64), side="right")

@@ -12,7 +12,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import gen_inputs as gi
-from multishiftseg_b200.evaluator import StreamingEvaluator, choose_splitters
+from multishiftseg_b200.evaluator import (StreamingEvaluator, choose_splitters, heavy_bins, range_estimates,
+                                          refine_splitters)
 from numpy_backend import NumpyBackend
 from oracle import c_oracle
 
@@ -27,6 +28,17 @@ def _free_port():
 
 CASES = [("cont", 20011, 0.1, 0.05), ("q2", 30007, 0.05, 0.2), ("const", 5000, 0.3, 0.0), ("f16", 40009, 0.01, 0.05),
          ("zeros", 9000, 0.3, 0.05)]
+
+
+def _narrow_case(n=30011):
+    """Scores in one top-16-bit key bin (0.999 .. 1.0) plus a saturated tie mass: the case bin-granular splitters cannot
+    balance (ADVICE r1 #2)."""
+    rng = np.random.default_rng(77)
+    s = (0.999 + 0.001 * rng.random(n)).astype(np.float32)
+    s[rng.random(n) < 0.2] = np.float32(0.9995)
+    l = (rng.random(n) < 0.1).astype(np.int64)
+    l[rng.random(n) < 0.05] = 255
+    return s, l
 
 
 def _worker(rank, world, port, q):
@@ -44,6 +56,11 @@ def _worker(rank, world, port, q):
             ev.update(s[a:b], l[a:b])
         r = ev.compute()
         out.append(None if r is None else tuple(float(v) for v in r))
+    s, l = _narrow_case()
+    ev = StreamingEvaluator(len(s), backend=NumpyBackend(), distributed=True)
+    ev.update(s[rank::world], l[rank::world])
+    r = ev.compute()
+    out.append(tuple(float(v) for v in r))
     # a rank with no data at all, and an all-ignored dataset
     ev = StreamingEvaluator(10, backend=NumpyBackend(), distributed=True)
     if rank == 0:
@@ -85,6 +102,7 @@ def test_distributed_equals_single_process_and_oracle(world):
         single = StreamingEvaluator(n, backend=NumpyBackend(), distributed=False)
         single.update(s, l)
         assert tuple(float(v) for v in single.compute()) == want[-1]
+    want.append(c_oracle.eval_ood_measure(*_narrow_case()))
     want.append((0.75, float.fromhex("0x1.aaaaaaaaaaaaap-1"), 0.5))     # K1
     want.append(None)
     want.append("Input contains NaN.")
@@ -110,3 +128,27 @@ def test_choose_splitters_properties():
     hist[12345] = 10 ** 9
     spl = choose_splitters(hist, 4)
     assert spl == sorted(spl)
+
+
+def test_refined_splitters_balance_a_single_heavy_bin():
+    from oracle import metrics_oracle
+    s, l = _narrow_case(200000)
+    keys = metrics_oracle.float_key_desc(s[l != 255]).astype(np.uint32)
+    hist = np.bincount(keys >> 16, minlength=1 << 16).astype(np.int64)
+    for world in (2, 4, 8):
+        coarse = choose_splitters(hist, world)
+        heavy = heavy_bins(hist, coarse, world)
+        assert heavy, "the narrow case must trigger the second level"
+        fine = {b: np.bincount(keys[(keys >> 16) == b] & 0xFFFF, minlength=1 << 16).astype(np.int64) for b in heavy}
+        spl = refine_splitters(hist, fine, world)
+        assert len(spl) == world - 1 and spl == sorted(spl)
+        dest = np.searchsorted(np.asarray(spl, dtype=np.uint64), keys.astype(np.uint64), side="right")
+        loads = np.bincount(dest, minlength=world)
+        biggest_tie = int(np.unique(keys, return_counts=True)[1].max())
+        assert loads.max() <= len(keys) // world + biggest_tie + 2, (world, loads.tolist())
+        est = range_estimates(hist, fine, spl)
+        assert sum(est) == len(keys)
+        assert all(abs(int(e) - int(c)) <= 2 for e, c in zip(est, loads)), (est, loads.tolist())
+        # without the second level one rank would own (almost) everything
+        d0 = np.searchsorted(np.asarray(coarse, dtype=np.uint64), keys.astype(np.uint64), side="right")
+        assert np.bincount(d0, minlength=world).max() > 0.9 * len(keys)

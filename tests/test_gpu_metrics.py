@@ -290,6 +290,32 @@ def test_keys_histogram_sampled(M):
         assert np.array_equal(hist.cpu().numpy(), np.bincount(sample >> 16, minlength=1 << 16))
 
 
+def test_keys_histogram_refine(M):
+    """Second level of the splitter histogram: low 16 bits of the keys under one top-16-bit prefix, same sampling."""
+    from multishiftseg_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(10)
+    n = 1_000_003
+    k = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    k[: 700_000] = (k[: 700_000] & np.uint32(0xFFFF)) | np.uint32(0xBF7F0000)  # 70 % of the keys under one prefix
+    k[: 100_000] = np.uint32(0xBF7F1234)                                       # and a tie mass inside it
+    k = rng.permutation(k)
+    kt = torch.from_numpy(k.view(np.int32)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    for prefix in [0xBF7F, 0x0000, 0xFFFF, 0x1234]:
+        for every in [1, 3, 64]:
+            hist = torch.full((1 << 16,), -1, dtype=torch.int64, device="cuda")
+            assert lib.mss_keys_histogram_refine(kt.data_ptr(), n, prefix, every, hist.data_ptr(), st) == 0
+            sample = k if every == 1 else k[: n - n % 4].reshape(-1, 4)[::every].reshape(-1)
+            sample = sample[(sample >> 16) == prefix]
+            assert np.array_equal(hist.cpu().numpy(), np.bincount(sample & 0xFFFF, minlength=1 << 16)), (prefix, every)
+    hist = torch.full((1 << 16,), -1, dtype=torch.int64, device="cuda")
+    assert lib.mss_keys_histogram_refine(0, 0, 5, 1, hist.data_ptr(), st) == 0      # empty input: zeros
+    assert int(hist.abs().sum()) == 0
+    assert lib.mss_keys_histogram_refine(kt.data_ptr(), n, 1 << 16, 1, hist.data_ptr(), st) != 0
+    assert lib.mss_keys_histogram_refine(kt.data_ptr(), n, 1, 0, hist.data_ptr(), st) != 0
+
+
 @pytest.mark.parametrize("parts", [1, 2, 3, 8, 16, 17, 200, 256])
 def test_partition_many_and_few_parts(M, parts):
     from multishiftseg_b200 import _lib as L
