@@ -19,6 +19,15 @@ for n in [int(a) for a in args] or [1<<21, 1<<23, 1<<25, 1<<27]:
     if mode == "f16": s = s.half().float()
     lab=(torch.rand(n,device="cuda",generator=g)<0.05).to(torch.uint8)
     buf=metric.PairBuffer(n,"cuda"); buf.append(s,lab); m,npos,_,_=buf.read_state()
+    def app():
+        buf.reset(); buf.append(s,lab)
+    t_a=ev(app)
+    lab64=lab.long()
+    def app64():
+        buf.reset(); buf.append(s,lab64)
+    t_a64=ev(app64)
+    del lab64
+    buf.reset(); buf.append(s,lab); m,npos,_,_=buf.read_state()
     k0=buf.keys.clone()
     lib=L.load(); nb=lib.mss_sort_keys_workspace_bytes(m); ws=torch.empty(nb,dtype=torch.uint8,device="cuda")
     st=torch.cuda.current_stream().cuda_stream
@@ -38,4 +47,4 @@ for n in [int(a) for a in args] or [1<<21, 1<<23, 1<<25, 1<<27]:
     for _ in range(5):
         t0=time.perf_counter(); r=metric.eval_ood_measure(s,lab); torch.cuda.synchronize(); ts.append((time.perf_counter()-t0)*1e3)
     t_e=sorted(ts)[2]
-    print(f"{mode} n={n:>10d} T={tps.numel():>10d} sort {t_s:8.3f} ms {m/t_s/1e6:7.2f} Gkeys/s ({m*36/t_s/1e6:7.0f} GB/s impl) | counts {t_c:7.3f} ms | tail {t_t:7.3f} ms | eval_ood_measure {t_e:8.3f} ms {n/t_e/1e3:8.1f} Mpix/s", flush=True)
+    print(f"{mode} n={n:>10d} T={tps.numel():>10d} append u8 {t_a:6.3f} ms ({(n*5+m*4)/t_a/1e6:5.0f} GB/s) i64 {t_a64:6.3f} ms | sort {t_s:8.3f} ms {m/t_s/1e6:7.2f} Gkeys/s ({m*36/t_s/1e6:7.0f} GB/s impl) | counts {t_c:7.3f} ms | tail {t_t:7.3f} ms | eval_ood_measure {t_e:8.3f} ms {n/t_e/1e3:8.1f} Mpix/s", flush=True)
