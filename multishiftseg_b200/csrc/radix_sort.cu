@@ -906,16 +906,20 @@ exchange_append_dev_kernel(const uint32_t *__restrict__ keys, long long capacity
     const long long n_neg = (long long)min(state->n_neg, (unsigned long long)capacity);
     const long long n_pos = (long long)min(state->n_pos, (unsigned long long)(capacity - n_neg));
     const unsigned tiles_neg = (unsigned)((n_neg + SORT_TILE - 1) / SORT_TILE), tiles_pos = (unsigned)((n_pos + SORT_TILE - 1) / SORT_TILE);
-    if (blockIdx.x >= tiles_neg + tiles_pos) return;
-    if (tid < SORT_WARPS * PB_MAX_PARTS) (&sm.warp_hist[0][0])[tid] = 0;
     if ((int)tid < nspl) sm.spl[tid] = __ldg(splitters + tid);
-    __syncthreads();
-    const bool positives = blockIdx.x >= tiles_neg;
-    const unsigned tile = positives ? blockIdx.x - tiles_neg : blockIdx.x;
-    const uint32_t *src = positives ? keys + (capacity - n_pos) : keys;
-    const long long n = positives ? n_pos : n_neg;
-    if ((long long)(tile + 1) * SORT_TILE <= n) exchange_tile<true>(sm, src, n, tile, positives, dst, nspl + 1, steps);
-    else exchange_tile<false>(sm, src, n, tile, positives, dst, nspl + 1, steps);
+    // grid-stride over the tiles: the host caps the grid (a few CTAs per SM) so that this kernel, which mostly waits for
+    // remote reservations, only ever holds a fraction of an SM's slots next to the scoring kernel it runs beside
+    for (unsigned t = blockIdx.x; t < tiles_neg + tiles_pos; t += gridDim.x) {
+        if (tid < SORT_WARPS * PB_MAX_PARTS) (&sm.warp_hist[0][0])[tid] = 0;
+        __syncthreads();
+        const bool positives = t >= tiles_neg;
+        const unsigned tile = positives ? t - tiles_neg : t;
+        const uint32_t *src = positives ? keys + (capacity - n_pos) : keys;
+        const long long n = positives ? n_pos : n_neg;
+        if ((long long)(tile + 1) * SORT_TILE <= n) exchange_tile<true>(sm, src, n, tile, positives, dst, nspl + 1, steps);
+        else exchange_tile<false>(sm, src, n, tile, positives, dst, nspl + 1, steps);
+        __syncthreads();                                   // the bulk copies have read the tile's shared memory (wait_group.read)
+    }
 }
 
 // accum += staging (counts, flags); staging = 0 -- the staging buffer is empty again for the next batch
@@ -1611,7 +1615,10 @@ extern "C" int mss_eval_exchange_stream(const mss_eval_buffers *staging, const u
                                                                                            status, tiles * sstride, sstride, counters);
         MSS_CHECK_LAUNCH();
     } else {
-        exchange_append_dev_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(staging->keys, staging->capacity,
+        // MSS_EXCHANGE_CTAS_PER_SM (default 1): resident CTAs of the streamed exchange per SM; 0 = one CTA per tile
+        static const int per_sm = [] { const char *e = getenv("MSS_EXCHANGE_CTAS_PER_SM"); return e ? atoi(e) : 1; }();
+        const unsigned grid = per_sm > 0 ? (unsigned)std::min<size_t>(tiles, (size_t)sm_count() * per_sm) : (unsigned)tiles;
+        exchange_append_dev_kernel<<<grid, SORT_THREADS, 0, st>>>(staging->keys, staging->capacity,
                                                                             (const EvalState *)staging->state, splitters_dev,
                                                                             parts - 1, steps, dst);
         MSS_CHECK_LAUNCH();

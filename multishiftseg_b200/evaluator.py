@@ -24,6 +24,7 @@ host/collective logic under gloo -- there is no CPU fallback in this package.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -403,7 +404,7 @@ class StreamingEvaluator:
             dev = be.device
             self._st = {"staging": [be.new_buffer(cap), be.new_buffer(cap)], "cap": cap, "n": 0, "calibrated": False,
                         "accum": torch.zeros(L.EVAL_STATE_BYTES, dtype=torch.uint8, device=dev),
-                        "side": torch.cuda.Stream(device=dev, priority=-1),
+                        "side": torch.cuda.Stream(device=dev, priority=int(os.environ.get("MSS_STREAM_PRIORITY", "-1"))),
                         "appended": [torch.cuda.Event(), torch.cuda.Event()], "done": [None, None]}
             for sb in self._st["staging"]:
                 sb.reset()

@@ -162,3 +162,71 @@ def test_forward_only_ops_refuse_grad_inputs_on_gpu():
     assert x.grad is not None and bool(torch.isfinite(x.grad).all())
     a = m2f.anomaly_score_from_lowres(cls, lo, (32, 64), (32, 64))
     assert a.grad_fn is not None
+
+
+# ---- evaluator append at sizes that take the 4096-pixel-tile kernel's fast path (whole tiles, 16-byte-aligned inputs)
+def _tup(r):
+    return None if r is None else tuple(float(x) for x in r)
+
+
+@pytest.mark.parametrize("ldt", ["uint8", "int32", "int64"])
+@pytest.mark.parametrize("n", [4096, 65536 + 1, 300_003])
+def test_append_label_dtypes_whole_tiles(ldt, n):
+    from multishiftseg_b200 import metric as M
+    s, l = gi.metric_case(40 + n % 7, n, "q2", 0.07, 0.1, label_dtype=ldt)
+    want = c_oracle.eval_ood_measure(s, l)
+    assert _tup(M.eval_ood_measure(torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda())) == want
+    # ids that are not 0 / 1, one of them outside the uint8 range (never matches a uint8 label)
+    l2 = np.where(l == 0, 7, np.where(l == 1, 3, l)).astype(l.dtype)
+    assert _tup(M.eval_ood_measure(torch.from_numpy(s).cuda(), torch.from_numpy(l2).cuda(), train_id_in=7, train_id_out=3)) == want
+    if ldt == "uint8":
+        assert M.eval_ood_measure(torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda(), train_id_in=0, train_id_out=256) is None
+
+
+def test_append_unaligned_views_match_aligned():
+    """Scores / labels that start 4 or 1 bytes into an allocation take the scalar kernel: same result."""
+    from multishiftseg_b200 import metric as M
+    s, l = gi.metric_case(51, 200_001, "cont", 0.05, 0.05, label_dtype="uint8")
+    want = c_oracle.eval_ood_measure(s[1:], l[1:])
+    st, lt = torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda()
+    assert _tup(M.eval_ood_measure(st[1:], lt[1:])) == want
+    assert _tup(M.eval_ood_measure(st[1:].clone(), lt[1:])) == want       # aligned scores, unaligned labels
+    assert _tup(M.eval_ood_measure(st[1:].clone(), lt[1:].clone())) == want
+
+
+def test_append_nonfinite_and_signed_zero_in_whole_tiles():
+    """sklearn's assert_all_finite semantics on the fast path: NaN / Inf in a VALID pixel raises (NaN first), in an
+    ignored pixel it does not; -0.0 and +0.0 are one threshold."""
+    from multishiftseg_b200 import metric as M
+    n = 150_000
+    s, l = gi.metric_case(52, n, "q2", 0.05, 0.1, label_dtype="uint8")
+    s = s.copy()
+    z = np.flatnonzero(l != 255)[:5000]
+    s[z[::2]] = 0.0
+    s[z[1::2]] = -0.0
+    want = c_oracle.eval_ood_measure(s, l)
+    run = lambda a: _tup(M.eval_ood_measure(torch.from_numpy(a).cuda(), torch.from_numpy(l).cuda()))
+    assert run(s) == want
+    ign, val = np.flatnonzero(l == 255), np.flatnonzero(l != 255)
+    a = s.copy(); a[ign[::3]] = np.nan; a[ign[1::3]] = np.inf; a[ign[2::3]] = -np.inf
+    assert run(a) == want
+    for pos in (val[0], val[len(val) // 2], val[-1]):
+        a = s.copy(); a[pos] = np.inf
+        with pytest.raises(ValueError, match="infinity"):
+            run(a)
+        a[pos] = -np.inf
+        with pytest.raises(ValueError, match="infinity"):
+            run(a)
+        a[val[7]] = np.nan
+        with pytest.raises(ValueError, match="NaN"):
+            run(a)
+
+
+def test_append_overflow_is_reported_not_written_past_the_buffer():
+    from multishiftseg_b200 import _lib as L, metric as M
+    s, l = gi.metric_case(53, 100_000, "cont", 0.05, 0.0, label_dtype="uint8")
+    buf = M.PairBuffer(50_000, "cuda")                                    # (tools/gpu_sanitize.sh runs this under memcheck)
+    buf.reset()
+    buf.append(torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda())
+    with pytest.raises(L.MssError):
+        buf.read_state()
