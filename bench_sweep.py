@@ -342,7 +342,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--continuous", type=int, default=0, help="also run the T ~= N metric-stage variant on this many frames")
     ap.add_argument("--no-oracle", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=("auto", "stream", "p2p", "p2p_counted", "nccl"),
+    ap.add_argument("--exchange", default="auto", choices=("auto", "stream", "stream_sm", "p2p", "p2p_counted", "nccl"),
                     help="multi-GPU exchange of StreamingEvaluator (stream = overlapped with the scoring)")
     args = ap.parse_args()
     if not torch.cuda.is_available():

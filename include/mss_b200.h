@@ -310,6 +310,26 @@ MSS_API size_t mss_eval_exchange_stream_workspace_bytes(int64_t staging_capacity
 MSS_API int mss_eval_exchange_stream(const mss_eval_buffers *staging, const uint32_t *splitters_dev, int parts,
                              const uint64_t *dst_keys_host, const uint64_t *dst_state_host, int64_t dst_capacity,
                              void *accum_state, void *workspace, size_t workspace_bytes, void *stream);
+/* Staged form (the copy engines move the keys): ENQUEUES, on `stream`,
+ *   1. the partition of a STAGING evaluator (sizes read from its device state) into `parts` LOCAL outbox buffers -- each an
+ *      evaluator layout of outbox_capacity keys (negatives up from key 0, positives down from the end) with its own
+ *      MSS_EVAL_STATE_BYTES state, zeroed here first;
+ *   2. ONE reservation per destination and stream in the owners' receive states (recv_state_host[d]: device address of
+ *      rank d's state, peer-mapped; system-scope atomicAdd) and the copy plan, written to `plan` (uint64[4 * parts], pinned
+ *      host memory or device memory):  plan[4d + 0], [4d + 1] = number of in-distribution keys for rank d and the key index
+ *      in rank d's receive buffer where that run starts;  [4d + 2], [4d + 3] the same for the OOD keys (the run occupies
+ *      the LAST plan[4d + 2] keys of outbox d).  A run that does not fit is dropped and the owner's overflow is raised;
+ *   3. accum_state += staging state; staging state = 0.
+ * After the work enqueued here has completed (event), the caller copies run d from outbox d to the owner's key buffer at
+ * the planned index -- e.g. mss_memcpy_async on another stream -- and may reuse the outboxes once those copies are done.
+ * This is what replaces test_deeplab.py:94-101's per-batch .cpu().numpy() + the final np.concatenate across GPUs. */
+MSS_API int mss_eval_exchange_stage(const mss_eval_buffers *staging, const uint32_t *splitters_dev, int parts,
+                            const uint64_t *outbox_keys_host, const uint64_t *outbox_state_host, int64_t outbox_capacity,
+                            const uint64_t *recv_state_host, int64_t recv_capacity, void *accum_state, uint64_t *plan,
+                            void *stream);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): device-to-device (also peer-mapped) block copy on the copy
+ * engines, for hosts that have no CUDA runtime binding of their own */
+MSS_API int mss_memcpy_async(void *dst, const void *src, size_t bytes, void *stream);
 /* two sorted key arrays (negatives = in-distribution, positives = OOD) -> per distinct key of their union the
  * cumulative counts  tps[k] = pos_before + #{positives with key <= key_k},  fps[k] = neg_before + #{negatives with
  * key <= key_k}  (int64; one merge-path pass).  tps/fps need room for n_neg + n_pos entries.  *T_host = number of

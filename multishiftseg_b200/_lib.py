@@ -88,6 +88,8 @@ SIGNATURES = {
     "mss_eval_exchange_append": (_i, [_EV, _i64, _i64, _p, _i, _p, _p, _i64, _p, _sz, _p]),
     "mss_eval_exchange_stream_workspace_bytes": (_sz, [_i64, _i]),
     "mss_eval_exchange_stream": (_i, [_EV, _p, _i, _p, _p, _i64, _p, _p, _sz, _p]),
+    "mss_eval_exchange_stage": (_i, [_EV, _p, _i, _p, _p, _i64, _p, _i64, _p, _p, _p]),
+    "mss_memcpy_async": (_i, [_p, _p, _sz, _p]),
     "mss_counts_workspace_bytes": (_sz, [_i64]),
     "mss_counts_from_sorted": (_i, [_p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "mss_tail_workspace_bytes": (_sz, [_i64]),

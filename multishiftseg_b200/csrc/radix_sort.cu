@@ -769,12 +769,33 @@ struct ExchangeDst {
     long long capacity;                        // keys per destination buffer
 };
 
-template <bool FULL>
+// Per-phase cycle counters of exchange_tile (development builds only: MSS_NVCC_EXTRA=-DMSS_EXCH_PROFILE; tools/exch_phases.py)
+#ifdef MSS_EXCH_PROFILE
+__device__ unsigned long long g_exch_prof[32];
+__device__ __forceinline__ unsigned long long prof_clock() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#define EXCH_T(var) const unsigned long long var = prof_clock()
+#define EXCH_ADD(i, d) atomicAdd(&g_exch_prof[i], (unsigned long long)(d))
+extern "C" MSS_API int mss_debug_exchange_profile(unsigned long long *out32_host, int reset) {
+    if (out32_host) cudaMemcpyFromSymbol(out32_host, g_exch_prof, sizeof(g_exch_prof));
+    if (reset) { unsigned long long z[32] = {}; cudaMemcpyToSymbol(g_exch_prof, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define EXCH_T(var)
+#define EXCH_ADD(i, d)
+#endif
+
+template <bool FULL, bool SMALL>
 __device__ __forceinline__ void exchange_tile(PartSmem &sm, const uint32_t *__restrict__ keys_in, long long n, unsigned tile,
                                               bool positives, const ExchangeDst &dst, int nd, int steps) {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_n = FULL ? SORT_TILE : (int)(n - (long long)tile * SORT_TILE);
     const SplitterDigit digit_of{sm.spl, nd - 1, steps};
+    EXCH_T(t0);
 
     uint32_t key[SORT_IPT];
     const int wbase = warp * (32 * SORT_IPT) + lane;
@@ -782,16 +803,67 @@ __device__ __forceinline__ void exchange_tile(PartSmem &sm, const uint32_t *__re
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) key[i] = (FULL || wbase + i * 32 < tile_n) ? __ldg(kp + i * 32) : 0u;
     unsigned dpk[SORT_IPT / 4];
+    unsigned *wh = sm.warp_hist[warp];
+    unsigned rank2[SORT_IPT / 2];
+    if (SMALL) {
+        // <= 8 destinations (round 2: the ballot ranking below costs 3.4 warp instructions per key, which made this kernel
+        // issue-bound at 250 Gkeys/s).  Count per thread instead -- 8-bit fields of a 64-bit word, a thread has 16 keys --
+        // widen to 16-bit fields, ONE packed warp scan (4 words), and a key's rank is its thread's exclusive offset for
+        // that destination plus a running count.  The order inside a destination becomes thread-major, which is as good
+        // as any: a stream is a multiset.
+        uint32_t sp[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) sp[j] = j < nd - 1 ? sm.spl[j] : 0xFFFFFFFFu;
+        unsigned long long c8 = 0;
+#pragma unroll
+        for (int i = 0; i < SORT_IPT; i++) {
+            unsigned d = 0;
+#pragma unroll
+            for (int j = 0; j < 7; j++) d += key[i] >= sp[j] ? 1u : 0u;
+            d = min(d, (unsigned)(nd - 1));                // (a key of 0xFFFFFFFF would pass the padding: a NaN, flagged anyway)
+            dpk[i >> 2] = (i & 3) ? (dpk[i >> 2] | (d << (8 * (i & 3)))) : d;
+            if (FULL || wbase + i * 32 < tile_n) c8 += 1ull << (8 * d);
+        }
+        // 16-bit fields: e[0] = (d0, d2), e[1] = (d1, d3), e[2] = (d4, d6), e[3] = (d5, d7)
+        const unsigned lo = (unsigned)c8, hi = (unsigned)(c8 >> 32);
+        unsigned c[4] = {lo & 0x00FF00FFu, (lo >> 8) & 0x00FF00FFu, hi & 0x00FF00FFu, (hi >> 8) & 0x00FF00FFu};
+        unsigned e[4] = {c[0], c[1], c[2], c[3]};
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, e[q], s2);
+                if (lane >= s2) e[q] += u;
+            }
+        }
+        if (lane == 31) {                                  // the warp's counts per destination
+            wh[0] = e[0] & 0xFFFFu; wh[2] = e[0] >> 16; wh[1] = e[1] & 0xFFFFu; wh[3] = e[1] >> 16;
+            wh[4] = e[2] & 0xFFFFu; wh[6] = e[2] >> 16; wh[5] = e[3] & 0xFFFFu; wh[7] = e[3] >> 16;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) e[q] -= c[q];          // exclusive: keys of the lower lanes, per destination
+#pragma unroll
+        for (int i = 0; i < SORT_IPT; i++) {
+            const unsigned d = (dpk[i >> 2] >> (8 * (i & 3))) & 255u;
+            const unsigned w = ((d >> 1) & 2u) | (d & 1u), sh = (d & 2u) << 3;      // word e[w], field at bit sh
+            const unsigned x = w == 0 ? e[0] : w == 1 ? e[1] : w == 2 ? e[2] : e[3];
+            const unsigned r16 = (x >> sh) & 0xFFFFu;
+            const unsigned inc = (FULL || wbase + i * 32 < tile_n) ? (1u << sh) : 0u;
+            e[0] += w == 0 ? inc : 0u; e[1] += w == 1 ? inc : 0u; e[2] += w == 2 ? inc : 0u; e[3] += w == 3 ? inc : 0u;
+            rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r16 << 16)) : r16;
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
         const unsigned d = digit_of(key[i]);
         dpk[i >> 2] = (i & 3) ? (dpk[i >> 2] | (d << (8 * (i & 3)))) : d;
     }
+    }
     auto dig = [&](int i) -> unsigned { return (dpk[i >> 2] >> (8 * (i & 3))) & 255u; };
+    EXCH_T(t1);                                            // keys loaded (the digits depend on them)
 
-    unsigned rank2[SORT_IPT / 2];
+    if (!SMALL) {
     const unsigned lt = lanemask_lt();
-    unsigned *wh = sm.warp_hist[warp];
 #pragma unroll
     for (int i = 0; i < SORT_IPT; i++) {
         const bool valid = FULL || wbase + i * 32 < tile_n;
@@ -814,7 +886,10 @@ __device__ __forceinline__ void exchange_tile(PartSmem &sm, const uint32_t *__re
         rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r16 << 16)) : r16;
         __syncwarp();
     }
+    }
+    EXCH_T(t2);                                            // ranked
     __syncthreads();
+    EXCH_T(t3);
 
     // thread d < nd: reserve this tile's run in destination d (one remote atomic), address of the run
     if ((int)tid < nd) {
@@ -836,8 +911,12 @@ __device__ __forceinline__ void exchange_tile(PartSmem &sm, const uint32_t *__re
         }
         sm.dst[d] = addr;
         sm.count[d] = tot;
+#ifdef MSS_EXCH_PROFILE
+        { EXCH_T(ta); EXCH_ADD(16 + d, ta - t3); }         // reservation round trip per destination
+#endif
     }
     __syncthreads();
+    EXCH_T(t4);
     if (tid == 0) {
         unsigned cur = 0;
         for (int d = 0; d < nd; d++) {
@@ -865,6 +944,7 @@ __device__ __forceinline__ void exchange_tile(PartSmem &sm, const uint32_t *__re
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    EXCH_T(t5);
     if ((int)tid < nd) {
         const unsigned cnt = sm.count[tid], st0 = sm.start[tid];
         const unsigned long long a = sm.dst[tid];
@@ -874,8 +954,26 @@ __device__ __forceinline__ void exchange_tile(PartSmem &sm, const uint32_t *__re
         if (body) bulk_store_1d(a + 4ull * head, smem_u32(&sm.keys[st0 + head]), body * 4u);
         for (unsigned j = head + body; j < cnt; j++) *reinterpret_cast<uint32_t *>(a + 4ull * j) = sm.keys[st0 + j];
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        EXCH_T(t6);
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#ifdef MSS_EXCH_PROFILE
+        { EXCH_T(t7); EXCH_ADD(24 + tid, t7 - t6); if (tid == 0) EXCH_ADD(6, t6 - t5); }   // bulk read-completion per destination
+#endif
     }
+#ifdef MSS_EXCH_PROFILE
+    if (tid == 0) {
+        EXCH_T(t8);
+        EXCH_ADD(0, t1 - t0); EXCH_ADD(1, t2 - t1); EXCH_ADD(2, t3 - t2); EXCH_ADD(3, t4 - t3); EXCH_ADD(4, t5 - t4);
+        EXCH_ADD(7, t8 - t0); EXCH_ADD(15, 1);
+    }
+#endif
+}
+
+template <bool FULL>
+__device__ __forceinline__ void exchange_tile_any(PartSmem &sm, const uint32_t *__restrict__ keys_in, long long n, unsigned tile,
+                                                  bool positives, const ExchangeDst &dst, int nd, int steps) {
+    if (nd <= 8) exchange_tile<FULL, true>(sm, keys_in, n, tile, positives, dst, nd, steps);
+    else exchange_tile<FULL, false>(sm, keys_in, n, tile, positives, dst, nd, steps);
 }
 
 // blockIdx.x < tiles_neg: a tile of the in-distribution stream, else of the OOD stream
@@ -891,8 +989,8 @@ exchange_append_kernel(const uint32_t *__restrict__ neg, long long n_neg, const 
     const unsigned tile = positives ? blockIdx.x - tiles_neg : blockIdx.x;
     const uint32_t *keys = positives ? pos : neg;
     const long long n = positives ? n_pos : n_neg;
-    if ((long long)(tile + 1) * SORT_TILE <= n) exchange_tile<true>(sm, keys, n, tile, positives, dst, nspl + 1, steps);
-    else exchange_tile<false>(sm, keys, n, tile, positives, dst, nspl + 1, steps);
+    if ((long long)(tile + 1) * SORT_TILE <= n) exchange_tile_any<true>(sm, keys, n, tile, positives, dst, nspl + 1, steps);
+    else exchange_tile_any<false>(sm, keys, n, tile, positives, dst, nspl + 1, steps);
 }
 
 // The same, with the stream sizes read from the source evaluator's DEVICE state: nothing on the host has to know how
@@ -916,8 +1014,8 @@ exchange_append_dev_kernel(const uint32_t *__restrict__ keys, long long capacity
         const unsigned tile = positives ? t - tiles_neg : t;
         const uint32_t *src = positives ? keys + (capacity - n_pos) : keys;
         const long long n = positives ? n_pos : n_neg;
-        if ((long long)(tile + 1) * SORT_TILE <= n) exchange_tile<true>(sm, src, n, tile, positives, dst, nspl + 1, steps);
-        else exchange_tile<false>(sm, src, n, tile, positives, dst, nspl + 1, steps);
+        if ((long long)(tile + 1) * SORT_TILE <= n) exchange_tile_any<true>(sm, src, n, tile, positives, dst, nspl + 1, steps);
+        else exchange_tile_any<false>(sm, src, n, tile, positives, dst, nspl + 1, steps);
         __syncthreads();                                   // the bulk copies have read the tile's shared memory (wait_group.read)
     }
 }
@@ -930,6 +1028,37 @@ __global__ void eval_state_fold_kernel(EvalState *accum, EvalState *staging) {
     accum->inf_flag |= staging->inf_flag;
     accum->overflow += staging->overflow;
     staging->n_neg = 0; staging->n_pos = 0; staging->nan_flag = 0; staging->inf_flag = 0; staging->overflow = 0;
+}
+
+// ---- streamed exchange through the copy engines ---------------------------------------------------------------
+// Measured on B200 (round 2, tools/probe_stream.py, 2 GPUs, 1.0 G keys per rank): the remote-append kernel beside the
+// scoring kernel costs the scoring loop +12 ms, the same kernel with LOCAL destinations +9 ms -- but it runs in 2.9 ms
+// when it has the GPU to itself (two issue-bound kernels sharing the SMs lose more than they overlap), and 8.6 ms alone
+// with remote destinations (NVLink at 230 GB/s: small runs, one round trip per tile).  So the staged form: partition a
+// batch into LOCAL per-destination outboxes right behind its scoring kernel, on the same stream; one thread per
+// (destination, stream) then reserves the run in the owner's receive buffer with a single system-scope atomicAdd and
+// writes (count, offset) to pinned host memory; the host hands the 2 x ranks block copies of the batch to the COPY
+// ENGINES (mss_memcpy_async), which move them over NVLink while the SMs score the next batch.
+__global__ void exchange_plan_kernel(ExchangeDst outbox, ExchangeDst recv, int parts, unsigned long long *plan) {
+    const int t = threadIdx.x;
+    if (t >= 2 * parts) return;
+    const int d = t >> 1, positives = t & 1;
+    EvalState *os = reinterpret_cast<EvalState *>(outbox.state[d]);
+    EvalState *rs = reinterpret_cast<EvalState *>(recv.state[d]);
+    unsigned long long cnt = positives ? os->n_pos : os->n_neg, off = 0;
+    if (!positives && os->overflow) atomicAdd_system(&rs->overflow, os->overflow);     // an outbox overflowed: the owner reports it
+    if (cnt) {
+        const unsigned long long base = atomicAdd_system(positives ? &rs->n_pos : &rs->n_neg, cnt);
+        if (base + cnt > (unsigned long long)recv.capacity) {
+            atomicAdd_system(&rs->overflow, cnt);                                       // dropped: the owner reports MSS_ERR_WORKSPACE
+            cnt = 0;
+        } else {
+            off = positives ? (unsigned long long)recv.capacity - base - cnt : base;    // first key of the run in the owner's buffer
+        }
+    }
+    plan[4 * d + 2 * positives] = cnt;
+    plan[4 * d + 2 * positives + 1] = off;
+    __threadfence_system();
 }
 
 // ---- streamed exchange without per-tile remote atomics ------------------------------------------------------
@@ -1625,5 +1754,48 @@ extern "C" int mss_eval_exchange_stream(const mss_eval_buffers *staging, const u
     }
     eval_state_fold_kernel<<<1, 1, 0, st>>>((EvalState *)accum_state, (EvalState *)staging->state);
     MSS_CHECK_LAUNCH();
+    return MSS_OK;
+}
+
+extern "C" int mss_eval_exchange_stage(const mss_eval_buffers *staging, const uint32_t *splitters_dev, int parts,
+                                       const uint64_t *outbox_keys_host, const uint64_t *outbox_state_host,
+                                       int64_t outbox_capacity, const uint64_t *recv_state_host, int64_t recv_capacity,
+                                       void *accum_state, uint64_t *plan, void *stream) {
+    MSS_REQUIRE(parts >= 1 && parts <= PB_MAX_PARTS, "mss_eval_exchange_stage: parts must be 1..%d", PB_MAX_PARTS);
+    MSS_REQUIRE(staging && staging->keys && staging->state && staging->capacity > 0 && accum_state && outbox_keys_host &&
+                    outbox_state_host && recv_state_host && plan && outbox_capacity > 0 && recv_capacity > 0 &&
+                    (parts == 1 || splitters_dev),
+                "mss_eval_exchange_stage: bad arguments");
+    ExchangeDst box, recv;
+    for (int j = 0; j < PB_MAX_PARTS; j++) { box.keys[j] = box.state[j] = recv.keys[j] = recv.state[j] = 0; }
+    for (int j = 0; j < parts; j++) {
+        MSS_REQUIRE(outbox_keys_host[j] && outbox_state_host[j] && recv_state_host[j] && (outbox_keys_host[j] & 15) == 0 &&
+                        (outbox_state_host[j] & 7) == 0 && (recv_state_host[j] & 7) == 0,
+                    "mss_eval_exchange_stage: bad buffer %d", j);
+        box.keys[j] = outbox_keys_host[j];
+        box.state[j] = outbox_state_host[j];
+        recv.state[j] = recv_state_host[j];
+    }
+    box.capacity = outbox_capacity;
+    recv.capacity = recv_capacity;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int j = 0; j < parts; j++) MSS_CHECK_CUDA(cudaMemsetAsync((void *)outbox_state_host[j], 0, MSS_EVAL_STATE_BYTES, st));
+    const size_t tiles = sort_tiles(staging->capacity) + 2;            // two streams: up to one partial tile each
+    MSS_REQUIRE(tiles < (1ull << 31), "mss_eval_exchange_stage: staging buffer too large");
+    exchange_append_dev_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(staging->keys, staging->capacity,
+                                                                        (const EvalState *)staging->state, splitters_dev,
+                                                                        parts - 1, splitter_steps(parts), box);
+    MSS_CHECK_LAUNCH();
+    exchange_plan_kernel<<<1, 2 * PB_MAX_PARTS, 0, st>>>(box, recv, parts, (unsigned long long *)plan);
+    MSS_CHECK_LAUNCH();
+    eval_state_fold_kernel<<<1, 1, 0, st>>>((EvalState *)accum_state, (EvalState *)staging->state);
+    MSS_CHECK_LAUNCH();
+    return MSS_OK;
+}
+
+extern "C" int mss_memcpy_async(void *dst, const void *src, size_t bytes, void *stream) {
+    if (bytes == 0) return MSS_OK;
+    MSS_REQUIRE(dst && src, "mss_memcpy_async: null pointer");
+    MSS_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return MSS_OK;
 }

@@ -202,6 +202,24 @@ class CudaBackend:
             L.check(lib.mss_eval_exchange_append(C.byref(buf.c), n_neg, n_pos, spl, parts, dk, ds, int(capacity), ws.data_ptr(),
                                                  4096, L.stream_ptr(self.device)), "mss_eval_exchange_append")
 
+    def exchange_stage(self, buf, spl_dev: torch.Tensor, parts: int, out_key_ptrs: Sequence[int], out_state_ptrs: Sequence[int],
+                       out_capacity: int, recv_state_ptrs: Sequence[int], recv_capacity: int, accum_state: torch.Tensor,
+                       plan: torch.Tensor):
+        """Enqueue (no host sync, current stream): partition a staging buffer into LOCAL outboxes, reserve the runs in the
+        owners' receive states, write the copy plan to ``plan`` (pinned int64[4 * parts]), fold the staging state."""
+        import ctypes as C
+        lib = L.load()
+        ok = (C.c_uint64 * parts)(*[int(x) for x in out_key_ptrs])
+        os_ = (C.c_uint64 * parts)(*[int(x) for x in out_state_ptrs])
+        rs = (C.c_uint64 * parts)(*[int(x) for x in recv_state_ptrs])
+        with torch.cuda.device(self.device):
+            L.check(lib.mss_eval_exchange_stage(C.byref(buf.c), spl_dev.data_ptr(), parts, ok, os_, int(out_capacity), rs,
+                                                int(recv_capacity), accum_state.data_ptr(), plan.data_ptr(),
+                                                L.stream_ptr(self.device)), "mss_eval_exchange_stage")
+
+    def memcpy_async(self, dst_ptr: int, src_ptr: int, nbytes: int, stream: torch.cuda.Stream):
+        L.check(L.load().mss_memcpy_async(int(dst_ptr), int(src_ptr), int(nbytes), stream.cuda_stream), "mss_memcpy_async")
+
     def exchange_stream(self, buf, spl_dev: torch.Tensor, parts: int, key_ptrs: Sequence[int], state_ptrs: Sequence[int],
                         capacity: int, accum_state: torch.Tensor, ws: Optional[torch.Tensor] = None):
         """Enqueue (no host sync, current stream) the remote append of a staging buffer -- sizes are read from its device
@@ -333,14 +351,16 @@ class StreamingEvaluator:
 
     def __init__(self, capacity: int, device=None, train_id_in: int = 0, train_id_out: int = 1, backend=None,
                  distributed: Optional[bool] = None, group=None, exchange: str = "auto", stage_capacity: Optional[int] = None):
-        """``exchange``: "stream" = every batch is exchanged (remote append over NVLink) on a side stream right behind the
-        kernel that scored it, while the next batch is scored -- ``compute`` then starts with the keys already at their
-        owners.  The key ranges are fixed from the FIRST batch (a collective inside the first ``update*`` call: every
-        rank must make one), ``reset`` is collective, and a rank receives about ``capacity`` keys (+25 %).
+        """``exchange``: "stream" = every batch is partitioned by owner right behind the kernel that scored it (local
+        outboxes, same stream) and its runs are moved to the owners' peer-mapped receive buffers by the COPY ENGINES while
+        the next batch is scored -- ``compute`` then starts with the keys already at their owners.  The key ranges are fixed
+        from the FIRST batch (a collective inside the first ``update*`` call: every rank must make one), ``reset`` is
+        collective, and a rank receives about ``capacity`` keys (+25 %).  "stream_sm" = the same with the SMs doing the
+        transfer (remote append kernel on a side stream; measured slower, kept for comparison).
         "p2p" = remote append into the owners' peer-mapped buffers over NVLink (no counting pass),
         "p2p_counted" = count + all-gather of bucket sizes + fused partition/peer stores at known offsets, "nccl" = local
         partition + all-to-all, "auto" = p2p when the backend offers peer buffers (falls back if mapping fails)."""
-        assert exchange in ("auto", "p2p", "p2p_counted", "nccl", "stream")
+        assert exchange in ("auto", "p2p", "p2p_counted", "nccl", "stream", "stream_sm")
         self.exchange = exchange
         self.capacity = int(capacity)
         self.stage_capacity = stage_capacity
@@ -394,7 +414,7 @@ class StreamingEvaluator:
 
     # ------------------------------------------------------------------ streaming exchange
     def _streaming(self) -> bool:
-        return self.exchange == "stream" and self.distributed
+        return self.exchange in ("stream", "stream_sm") and self.distributed
 
     def _stage(self, numel: int):
         """-> (index, staging buffer) that the current stream may append ``numel`` pixels into."""
@@ -469,11 +489,63 @@ class StreamingEvaluator:
         dist.barrier(group=g)
         st["calibrated"] = True
 
+    def _ce_push(self, b: int):
+        """exchange="stream": stage batch ``b`` (partition into local outboxes + reservations + copy plan) on the current
+        stream, then hand the PREVIOUS batch's runs to the copy engines -- the host waits for that batch's plan while the
+        GPU is busy with this one."""
+        import torch.distributed as dist
+        be, st = self.backend, self._st
+        world = dist.get_world_size(self.group)
+        pb = st["pb"]
+        if "out_keys" not in st:
+            cap_o = st["cap_o"] = (st["cap"] + 3) // 4 * 4                # worst case: a whole batch for one owner (16-byte rows)
+            st["out_keys"] = [be.empty(world * cap_o, torch.int32).view(world, cap_o) for _ in range(2)]
+            st["out_state"] = [torch.zeros((world, L.EVAL_STATE_BYTES), dtype=torch.uint8, device=be.device) for _ in range(2)]
+            st["plan"] = [torch.zeros(4 * world, dtype=torch.int64).pin_memory() for _ in range(2)]
+            st["planned"], st["copied"], st["pending"], st["n_ce"] = [None, None], [None, None], None, 0
+        p = st["n_ce"] & 1
+        st["n_ce"] += 1
+        cur = torch.cuda.current_stream(be.device)
+        if st["copied"][p] is not None:
+            cur.wait_event(st["copied"][p])                               # the copies that last read outbox p
+        cap_o = st["cap_o"]
+        ok = [st["out_keys"][p][d].data_ptr() for d in range(world)]
+        os_ = [st["out_state"][p][d].data_ptr() for d in range(world)]
+        be.exchange_stage(st["staging"][b], st["spl_dev"], world, ok, os_, cap_o, pb["state_ptrs"], pb["cap"], st["accum"],
+                          st["plan"][p])
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        st["planned"][p] = ev
+        if st["pending"] is not None:
+            self._ce_flush(st["pending"])
+        st["pending"] = p
+
+    def _ce_flush(self, p: int):
+        import torch.distributed as dist
+        be, st = self.backend, self._st
+        world = dist.get_world_size(self.group)
+        pb, cap_o, side = st["pb"], st["cap_o"], st["side"]
+        st["planned"][p].synchronize()
+        plan = st["plan"][p].tolist()
+        for d in range(world):
+            cn, on, cp, op = plan[4 * d: 4 * d + 4]
+            src = st["out_keys"][p][d].data_ptr()
+            if cn:
+                be.memcpy_async(pb["key_ptrs"][d] + 4 * on, src, 4 * cn, side)
+            if cp:
+                be.memcpy_async(pb["key_ptrs"][d] + 4 * op, src + 4 * (cap_o - cp), 4 * cp, side)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        st["copied"][p] = ev
+        st["pending"] = None
+
     def _stream_push(self, b: int):
         import torch.distributed as dist
         be, st = self.backend, self._st
         if not st["calibrated"]:
             self._stream_calibrate(st["staging"][b])
+        if self.exchange == "stream":
+            return self._ce_push(b)
         cur = torch.cuda.current_stream(be.device)
         st["appended"][b].record(cur)
         st["side"].wait_event(st["appended"][b])
@@ -497,9 +569,13 @@ class StreamingEvaluator:
     def _stream_reset(self):
         import torch.distributed as dist
         be, st = self.backend, self._st
+        if st.get("pending") is not None:
+            self._ce_flush(st["pending"])
         st["side"].synchronize()
         st["n"] = 0
         st["done"] = [None, None]
+        if "planned" in st:
+            st["planned"], st["copied"], st["pending"], st["n_ce"] = [None, None], [None, None], None, 0
         st["accum"].zero_()
         for sb in st["staging"]:
             sb.reset()
@@ -532,6 +608,8 @@ class StreamingEvaluator:
 
         if st is None or not st["calibrated"]:
             raise L.MssError('exchange="stream": compute() before any update (every rank must feed at least one batch)')
+        if st.get("pending") is not None:
+            self._ce_flush(st["pending"])                                 # the last batch's runs
         st["side"].synchronize()
         torch.cuda.synchronize(be.device)
         dist.barrier(group=g)                                             # every rank's appends have landed
@@ -561,7 +639,7 @@ class StreamingEvaluator:
         r_neg, r_pos = st["pb"]["buf"].streams(m2, m2_pos)
         return self._sort_count_tail(r_neg, m2 - m2_pos, r_pos, m2_pos, per_dst, recall_level, marks, mark,
                                      {"send_counts": None, "recv_counts": [[m2 - m2_pos], [m2_pos]],
-                                      "splitters": st["splitters"], "exchange": "stream"})
+                                      "splitters": st["splitters"], "exchange": self.exchange})
 
     def _peer_buffers(self, need: int, g, tag=None):
         """Peer-mapped receive buffer of >= need keys on every rank, or None (on EVERY rank) if it cannot be had.

@@ -64,17 +64,19 @@ def main():
         img = max(n // 16, 1)
         chunks = [(i, min(i + img, n)) for i in range(0, n, img)]
         want = c_oracle.eval_ood_measure(s, l)
-        ev = StreamingEvaluator(n // world + 2 * img, distributed=True, exchange="stream", stage_capacity=img + 16)
-        for rep in range(2):                                   # a second round after reset() reuses ranges and buffers
-            ev.reset()
-            for a, b in chunks[rank::world]:
-                ev.update(torch.from_numpy(s[a:b]).cuda(), torch.from_numpy(l[a:b]).cuda())
-            got = ev.compute()
-            got = None if got is None else tuple(float(v) for v in got)
-            good = got == want
-            ok &= good
-            if rank == 0:
-                print(f"[world {world}] {mode:6s} n={n:8d} stream round {rep} multi-gpu == oracle: {good}  {got}", flush=True)
+        for exch in ("stream", "stream_sm"):                       # copy-engine staged / remote-append kernel on a side stream
+            ev = StreamingEvaluator(n // world + 2 * img, distributed=True, exchange=exch, stage_capacity=img + 16)
+            for rep in range(2):                               # a second round after reset() reuses ranges and buffers
+                ev.reset()
+                for a, b in chunks[rank::world]:
+                    ev.update(torch.from_numpy(s[a:b]).cuda(), torch.from_numpy(l[a:b]).cuda())
+                got = ev.compute()
+                got = None if got is None else tuple(float(v) for v in got)
+                good = got == want
+                ok &= good
+                if rank == 0:
+                    print(f"[world {world}] {mode:6s} n={n:8d} {exch} round {rep} multi-gpu == oracle: {good}  {got}", flush=True)
+            del ev
     # fused DeepLab scoring -> evaluator, sharded images
     g = torch.Generator().manual_seed(7)
     B, H, W = 4, 128, 256

@@ -1,0 +1,5 @@
+#!/bin/bash
+N=$1
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py > gpurun_out/dist_check_n${N}_ce.log 2>&1; echo "dist_check rc=$?"; grep -c "True" gpurun_out/dist_check_n${N}_ce.log; grep "False\|rror" gpurun_out/dist_check_n${N}_ce.log | cut -c1-200 | tail
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 tests/dist_c_abi_check.py > gpurun_out/dist_c_abi_n${N}_ce.log 2>&1; echo "c_abi rc=$?"
