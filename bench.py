@@ -745,9 +745,10 @@ def main():
         import bench_sweep
         env = bench_sweep.Env(dist, rank, world, local)
         try:
-            # N > 1: exchange="stream" -- every batch goes to its owners over NVLink right behind its scoring kernel
+            # N > 1: exchange="stream" -- every batch is partitioned by owner right behind its scoring kernel and moved
+            # over NVLink by the copy engines while the next batch is scored (MSS_BENCH_EXCHANGE overrides, for A/B runs)
             sweep = bench_sweep.run_cfg4(env, args.sweep_images, steps=3, warmup=1, oracle_check=True,
-                                         exchange="stream" if world > 1 else "auto")
+                                         exchange=os.environ.get("MSS_BENCH_EXCHANGE", "stream") if world > 1 else "auto")
             cont = bench_sweep.run_continuous(env, args.continuous_frames, steps=3, warmup=1)
             if rank == 0:
                 extra["eval_sweep"] = sweep

@@ -1779,7 +1779,13 @@ extern "C" int mss_eval_exchange_stage(const mss_eval_buffers *staging, const ui
     box.capacity = outbox_capacity;
     recv.capacity = recv_capacity;
     cudaStream_t st = (cudaStream_t)stream;
-    for (int j = 0; j < parts; j++) MSS_CHECK_CUDA(cudaMemsetAsync((void *)outbox_state_host[j], 0, MSS_EVAL_STATE_BYTES, st));
+    bool packed = true;                                                 // states back to back: one memset instead of `parts`
+    for (int j = 1; j < parts; j++) packed &= outbox_state_host[j] == outbox_state_host[j - 1] + MSS_EVAL_STATE_BYTES;
+    if (packed) {
+        MSS_CHECK_CUDA(cudaMemsetAsync((void *)outbox_state_host[0], 0, (size_t)parts * MSS_EVAL_STATE_BYTES, st));
+    } else {
+        for (int j = 0; j < parts; j++) MSS_CHECK_CUDA(cudaMemsetAsync((void *)outbox_state_host[j], 0, MSS_EVAL_STATE_BYTES, st));
+    }
     const size_t tiles = sort_tiles(staging->capacity) + 2;            // two streams: up to one partial tile each
     MSS_REQUIRE(tiles < (1ull << 31), "mss_eval_exchange_stage: staging buffer too large");
     exchange_append_dev_kernel<<<(unsigned)tiles, SORT_THREADS, 0, st>>>(staging->keys, staging->capacity,

@@ -503,11 +503,13 @@ class StreamingEvaluator:
             st["out_state"] = [torch.zeros((world, L.EVAL_STATE_BYTES), dtype=torch.uint8, device=be.device) for _ in range(2)]
             st["plan"] = [torch.zeros(4 * world, dtype=torch.int64).pin_memory() for _ in range(2)]
             st["planned"], st["copied"], st["pending"], st["n_ce"] = [None, None], [None, None], None, 0
+            # a few copy streams, so that the runs of a batch travel on several copy engines at once
+            st["sides"] = [st["side"]] + [torch.cuda.Stream(device=be.device) for _ in range(min(3, max(world - 1, 0)))]
         p = st["n_ce"] & 1
         st["n_ce"] += 1
         cur = torch.cuda.current_stream(be.device)
-        if st["copied"][p] is not None:
-            cur.wait_event(st["copied"][p])                               # the copies that last read outbox p
+        for ev in st["copied"][p] or ():
+            cur.wait_event(ev)                                            # the copies that last read outbox p
         cap_o = st["cap_o"]
         ok = [st["out_keys"][p][d].data_ptr() for d in range(world)]
         os_ = [st["out_state"][p][d].data_ptr() for d in range(world)]
@@ -524,19 +526,25 @@ class StreamingEvaluator:
         import torch.distributed as dist
         be, st = self.backend, self._st
         world = dist.get_world_size(self.group)
-        pb, cap_o, side = st["pb"], st["cap_o"], st["side"]
+        pb, cap_o, sides = st["pb"], st["cap_o"], st["sides"]
+        rank = dist.get_rank(self.group)
         st["planned"][p].synchronize()
         plan = st["plan"][p].tolist()
-        for d in range(world):
+        for i in range(world):
+            d = (rank + 1 + i) % world                                   # every rank starts with another owner; its own run last
+            side = sides[i % len(sides)]
             cn, on, cp, op = plan[4 * d: 4 * d + 4]
             src = st["out_keys"][p][d].data_ptr()
             if cn:
                 be.memcpy_async(pb["key_ptrs"][d] + 4 * on, src, 4 * cn, side)
             if cp:
                 be.memcpy_async(pb["key_ptrs"][d] + 4 * op, src + 4 * (cap_o - cp), 4 * cp, side)
-        ev = torch.cuda.Event()
-        ev.record(side)
-        st["copied"][p] = ev
+        evs = []
+        for side in sides:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            evs.append(ev)
+        st["copied"][p] = evs
         st["pending"] = None
 
     def _stream_push(self, b: int):
@@ -571,7 +579,8 @@ class StreamingEvaluator:
         be, st = self.backend, self._st
         if st.get("pending") is not None:
             self._ce_flush(st["pending"])
-        st["side"].synchronize()
+        for sd in st.get("sides", [st["side"]]):
+            sd.synchronize()
         st["n"] = 0
         st["done"] = [None, None]
         if "planned" in st:
@@ -610,7 +619,8 @@ class StreamingEvaluator:
             raise L.MssError('exchange="stream": compute() before any update (every rank must feed at least one batch)')
         if st.get("pending") is not None:
             self._ce_flush(st["pending"])                                 # the last batch's runs
-        st["side"].synchronize()
+        for sd in st.get("sides", [st["side"]]):
+            sd.synchronize()
         torch.cuda.synchronize(be.device)
         dist.barrier(group=g)                                             # every rank's appends have landed
         acc = st["accum"].cpu().numpy()
