@@ -11,10 +11,14 @@ Multi-GPU (one process per GPU, images sharded over ranks, ``torch.distributed``
 step of the whole path.  Integer-exact, so the N-GPU result is bit-identical to the 1-GPU result:
 
   1. all_reduce of (count, positives, nan, inf)                          -> None / ValueError decisions
-  2. all_reduce of a 2^16-bin histogram of the top key bits              -> identical splitters everywhere
-  3. local stable partition by key range + all_to_all of (key, label)    -> rank r owns key range r
-     (a distinct score never straddles two ranks)
-  4. local radix sort, run-length counts with global (index, positives) prefixes from an all_gather
+  2. all_reduce of a 2^16-bin histogram of the top key bits (+ a second level inside heavy bins)
+                                                                         -> identical splitters everywhere
+  3. exchange by key range: rank r owns key range r, a distinct score never straddles two ranks.  The keys travel
+     as two key-only streams (in-distribution / OOD; the label is the stream) into the owner's peer-mapped buffer:
+     "stream" (per batch, behind the scoring kernel: local partition + copy engines), "stream_sm", "p2p",
+     "p2p_counted", or "nccl" (partition + all_to_all) -- see StreamingEvaluator.__init__ and DESIGN.md section 5
+  4. local radix sort of both streams, merge-path counts with the global (negatives, positives) prefixes of the
+     lower ranks, known from the all-gathered stream sizes
   5. all_gather of the per-threshold int64 (tps, fps)                     -> every rank runs the same float64
      tail on the same integers as a single GPU would
 
