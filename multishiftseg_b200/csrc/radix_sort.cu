@@ -854,38 +854,38 @@ __device__ __forceinline__ void exchange_tile(PartSmem &sm, const uint32_t *__re
         }
     } else {
 #pragma unroll
-    for (int i = 0; i < SORT_IPT; i++) {
-        const unsigned d = digit_of(key[i]);
-        dpk[i >> 2] = (i & 3) ? (dpk[i >> 2] | (d << (8 * (i & 3)))) : d;
-    }
+        for (int i = 0; i < SORT_IPT; i++) {
+            const unsigned d = digit_of(key[i]);
+            dpk[i >> 2] = (i & 3) ? (dpk[i >> 2] | (d << (8 * (i & 3)))) : d;
+        }
     }
     auto dig = [&](int i) -> unsigned { return (dpk[i >> 2] >> (8 * (i & 3))) & 255u; };
     EXCH_T(t1);                                            // keys loaded (the digits depend on them)
 
     if (!SMALL) {
-    const unsigned lt = lanemask_lt();
+        const unsigned lt = lanemask_lt();
 #pragma unroll
-    for (int i = 0; i < SORT_IPT; i++) {
-        const bool valid = FULL || wbase + i * 32 < tile_n;
-        const unsigned d = valid ? dig(i) : 0u;
-        unsigned pm = __ballot_sync(0xffffffffu, valid);
-        if (!valid) pm = ~pm;
-        for (int b = 0; b < steps; b++) {
-            const bool bit = (d >> b) & 1u;
-            const unsigned mm = __ballot_sync(0xffffffffu, bit);
-            pm &= bit ? mm : ~mm;
+        for (int i = 0; i < SORT_IPT; i++) {
+            const bool valid = FULL || wbase + i * 32 < tile_n;
+            const unsigned d = valid ? dig(i) : 0u;
+            unsigned pm = __ballot_sync(0xffffffffu, valid);
+            if (!valid) pm = ~pm;
+            for (int b = 0; b < steps; b++) {
+                const bool bit = (d >> b) & 1u;
+                const unsigned mm = __ballot_sync(0xffffffffu, bit);
+                pm &= bit ? mm : ~mm;
+            }
+            const unsigned below = __popc(pm & lt);
+            unsigned old = 0;
+            if (below == 0 && valid) {
+                old = wh[d];
+                wh[d] = old + __popc(pm);
+            }
+            old = __shfl_sync(0xffffffffu, old, __ffs(pm) - 1);
+            const unsigned r16 = old + below;
+            rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r16 << 16)) : r16;
+            __syncwarp();
         }
-        const unsigned below = __popc(pm & lt);
-        unsigned old = 0;
-        if (below == 0 && valid) {
-            old = wh[d];
-            wh[d] = old + __popc(pm);
-        }
-        old = __shfl_sync(0xffffffffu, old, __ffs(pm) - 1);
-        const unsigned r16 = old + below;
-        rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r16 << 16)) : r16;
-        __syncwarp();
-    }
     }
     EXCH_T(t2);                                            // ranked
     __syncthreads();
