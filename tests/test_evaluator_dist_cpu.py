@@ -152,3 +152,70 @@ def test_refined_splitters_balance_a_single_heavy_bin():
         # without the second level one rank would own (almost) everything
         d0 = np.searchsorted(np.asarray(coarse, dtype=np.uint64), keys.astype(np.uint64), side="right")
         assert np.bincount(d0, minlength=world).max() > 0.9 * len(keys)
+
+
+# ---- the STREAMED exchange (what bench.py runs for N > 1) under gloo: shared memory stands in for the peer-mapped
+#      buffers, a file lock for the system-scope atomics, memmove for the copy engines (tests/fake_peer_backend.py)
+def _stream_worker(rank, world, port, lock_path, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import fake_peer_backend as fp
+    fp.install_cuda_stubs()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    be = fp.FakePeerBackend(lock_path)
+    out = []
+    try:
+        for ci, (mode, n, p_ood, p_ign) in enumerate(CASES[:4]):
+            s, l = gi.metric_case(100 + ci, n, mode, p_ood, p_ign)
+            img = 1003                                              # not a multiple of 4: outbox rows get padded
+            chunks = [(i, min(i + img, n)) for i in range(0, n, img)]
+            ev = StreamingEvaluator(n // world + 4 * img, backend=be, distributed=True, exchange="stream", stage_capacity=img)
+            for rep in range(2):                                    # the second round reuses key ranges and buffers
+                ev.reset()
+                mine = chunks[rank::world]
+                if rep == 1 and rank == world - 1:
+                    mine = mine[::-1]                               # another arrival order, same multiset
+                for a, b in mine:
+                    ev.update(s[a:b], l[a:b])
+                if rank == 0:                                       # a batch without a single valid pixel
+                    ev.update(np.zeros(7, np.float32), np.full(7, 255))
+                r = ev.compute()
+                out.append(None if r is None else tuple(float(v) for v in r))
+            out.append(("refined", bool(ev._st and ev._st.get("splitters"))))
+        out.append(("copies", be.copies > 0))
+        # a batch larger than the staging capacity is refused (before anything collective happens)
+        s, l = gi.metric_case(100, 20011, "cont", 0.1, 0.05)
+        ev = StreamingEvaluator(2000, backend=be, distributed=True, exchange="stream", stage_capacity=100)
+        try:
+            ev.update(s[:1003], l[:1003])
+            out.append("no error")
+        except Exception as e:
+            out.append(type(e).__name__)
+    finally:
+        q.put((rank, out))
+        dist.barrier()
+        dist.destroy_process_group()
+        be.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_streamed_exchange_host_logic_equals_oracle(world, tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    lock = str(tmp_path / "atomics.lock")
+    procs = [ctx.Process(target=_stream_worker, args=(r, world, port, lock, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = []
+    for ci, (mode, n, p_ood, p_ign) in enumerate(CASES[:4]):
+        s, l = gi.metric_case(100 + ci, n, mode, p_ood, p_ign)
+        w = c_oracle.eval_ood_measure(s, l)
+        want += [w, w, ("refined", True)]
+    want += [("copies", True), "MssError"]
+    for r in range(world):
+        assert results[r] == want, (r, results[r], want)
